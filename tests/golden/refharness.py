@@ -1,0 +1,115 @@
+"""Run the UNMODIFIED reference env (/root/reference/SPaRC_Gym/SPaRC_Gym.py) in this
+container, to pin the oracle and to generate the golden vectors under tests/golden/.
+
+The reference needs `gymnasium` and `pygame` (not installed, no network) and downloads
+its puzzles from the HF hub (SPaRC_Gym.py:77).  Recipe:
+
+* inert stub modules for `gymnasium` (Env.reset seeds `self.np_random` with
+  `np.random.default_rng(seed)` -- the same PCG64(SeedSequence(seed)) stream gymnasium
+  uses), `gymnasium.spaces`, `gymnasium.envs.registration` and `pygame`;
+* `datasets.load_dataset` monkey-patched to hand back our rows as a DataFrame.
+
+Nothing here is importable on the GPU box (`/root/reference` does not exist there):
+only `make_golden.py` and tests marked `reference` use it, and they skip when the
+reference is absent.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import types
+
+import numpy as np
+
+REFERENCE_ROOT = os.environ.get("SPARC_REFERENCE_ROOT", "/root/reference")
+
+
+def reference_available():
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "SPaRC_Gym", "SPaRC_Gym.py"))
+
+
+def _install_stubs():
+    if "gymnasium" in sys.modules and not getattr(sys.modules["gymnasium"], "_SPARC_STUB", False):
+        return  # the real gymnasium is importable: use it
+    gym = types.ModuleType("gymnasium")
+    gym._SPARC_STUB = True
+
+    class Env:
+        np_random = None
+        metadata = {}
+
+        def reset(self, *, seed=None, options=None):
+            if seed is not None or self.np_random is None:
+                self.np_random = np.random.default_rng(seed)
+
+        def close(self):
+            pass
+
+    class _Space:
+        def __init__(self, *a, **k):
+            self.args, self.kwargs = a, k
+
+    spaces = types.ModuleType("gymnasium.spaces")
+    for name in ("Dict", "Box", "Text", "Discrete"):
+        setattr(spaces, name, type(name, (_Space,), {}))
+    envs = types.ModuleType("gymnasium.envs")
+    registration = types.ModuleType("gymnasium.envs.registration")
+    registry = {}
+
+    def register(id, entry_point=None, **kw):
+        registry[id] = entry_point
+
+    registration.register = register
+    registration.registry = registry
+    envs.registration = registration
+    gym.Env, gym.spaces, gym.envs = Env, spaces, envs
+    sys.modules.update({"gymnasium": gym, "gymnasium.spaces": spaces, "gymnasium.envs": envs,
+                        "gymnasium.envs.registration": registration})
+    if "pygame" not in sys.modules:
+        sys.modules["pygame"] = types.ModuleType("pygame")
+
+
+class _FakeDataset:
+    def __init__(self, rows):
+        self.rows = rows
+
+    def to_pandas(self):
+        import pandas as pd
+        return pd.DataFrame(self.rows)
+
+
+def load_reference_class():
+    """Import the reference package and return its SPaRC_Gym class."""
+    if not reference_available():
+        raise RuntimeError(f"reference not found under {REFERENCE_ROOT}")
+    try:
+        import gymnasium  # noqa: F401  (real one, if it exists)
+    except ImportError:
+        _install_stubs()
+    try:
+        import pygame  # noqa: F401
+    except ImportError:
+        sys.modules["pygame"] = types.ModuleType("pygame")
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+    import importlib
+    importlib.import_module("SPaRC_Gym")
+    # the package __init__ rebinds the name `SPaRC_Gym.SPaRC_Gym` to the class; the module
+    # itself (where `load_dataset` must be patched) is in sys.modules
+    return sys.modules["SPaRC_Gym.SPaRC_Gym"]
+
+
+def make_reference_env(rows, **kwargs):
+    """`SPaRC_Gym(**kwargs)` of the reference over `rows` (dataset-schema dicts)."""
+    ref_mod = load_reference_class()
+    ref_mod.load_dataset = lambda *a, **k: _FakeDataset(rows)
+    return ref_mod.SPaRC_Gym(**kwargs)
+
+
+def zero_leak(env, index=None):
+    """Undo the reference's state leak across episodes (SPaRC_Gym.py:149-151,
+    185-187): the cached `visited` / `agent_location` planes are never cleared."""
+    idxs = range(len(env.puzzles)) if index is None else [index]
+    for i in idxs:
+        for k in ("visited", "agent_location"):
+            env.puzzles[i]["obs_array"][k][...] = 0
