@@ -1,0 +1,292 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/s of the B200 SPaRC environment (BASELINE.json `metric`).
+
+    python bench.py --gpus N --steps K --warmup W          (N>1: launched by torchrun, one rank/GPU)
+    python bench.py --impl reference ...                   (the reference's CPU algorithm, host cores)
+
+A "step" is one lockstep pass of the hot path over all envs of the workload: actions ->
+dynamics -> terminal rule validation -> autoreset -> full rewrite of the 'new' observation
+(int32 base planes, int32 colour, int64 additional_info) into preallocated torch tensors.
+
+Default workload = BASELINE.json configs[3] ("1M envs, 6x6 full rule set with 8 colors, sharded
+across 8xB200"), i.e. the configuration the north-star target (>=1e9 steps/s on 8 GPUs at >=50%
+of HBM roofline, 6x6 full-rule puzzles) is quoted on: 131,072 envs PER GPU (weak scaling), pool of
+4,096 synthetic 6x6 puzzles.  `--workload config2|config3` select the other GPU configs.
+Prints ONE JSON line (see README / DESIGN.md for the keys).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (config id, envs per GPU, pool size, traceback, max_steps, description)
+    "config2": (2, 4096, 64, False, 1000, "4,096 lockstep envs, 4x4 gaps+dots puzzles (9x9 lattice, 5 planes)"),
+    "config3": (3, 65536, 1024, True, 1000, "65,536 envs, mixed 3x3-6x6 full-rule puzzles padded to 13x13, traceback, terminal validation"),
+    "config4": (4, 131072, 4096, False, 1000, "131,072 envs per GPU (1M on 8 GPUs), 6x6 full rule set, 8 colours (13x13 lattice, 10 planes)"),
+}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.1)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(r[2 + k].lower() == "active" for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference's algorithm (oracle port, reference_cost=True) on the host cores
+# ------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    rows, traceback, max_steps, budget_s, seed = args
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import sparc_oracle as so
+    env = so.OracleEnv(rows, observation="new", traceback=traceback, max_steps=max_steps, reference_cost=True)
+    rng = np.random.default_rng(seed)
+    k = 0
+    env.reset(options={"puzzle_id": rows[0]["id"]})
+    acts = rng.integers(0, 4, 1 << 16)
+    n = 0
+    t0 = time.perf_counter()
+    while time.perf_counter() - t0 < budget_s:
+        _, _, te, tr, _ = env.step(int(acts[n & 0xFFFF]))
+        n += 1
+        if te or tr:
+            k = (k + 1) % len(rows)
+            env.reset(options={"puzzle_id": rows[k]["id"]})
+    return n, time.perf_counter() - t0
+
+
+def cpu_baseline(workload, budget_s=12.0, cores=None):
+    """Oracle port of the reference env (two validations per step etc., like SG.py:1111-1238), one
+    env per worker process on every host core -- AsyncVectorEnv's architecture (gymnasium itself
+    is not installed on these boxes)."""
+    import multiprocessing as mp
+    from sparc_gym_b200.dataset import config_pool
+    cfg, _, _, traceback, max_steps, _ = WORKLOADS[workload]
+    cores = cores or os.cpu_count() or 1
+    rows = config_pool(cfg, n_puzzles=8 * cores)       # bounded sample of the pool: 8 puzzles per worker
+    jobs = [(rows[8 * w:8 * w + 8], traceback, max_steps, budget_s, w) for w in range(cores)]
+    t0 = time.perf_counter()
+    with mp.get_context("fork").Pool(cores) as pool:
+        res = pool.map(_cpu_worker, jobs)
+    wall = time.perf_counter() - t0
+    steps = sum(r[0] for r in res)
+    rate = sum(r[0] / r[1] for r in res)
+    return {"value": round(rate, 1), "unit": "env-steps/s", "cores": cores, "kind": "port",
+            "sample": f"{steps} random-action steps of the {workload} puzzles ({8 * cores} of the pool), one oracle env "
+                      f"(oracle/sparc_oracle.py, reference_cost=True) per worker process, {budget_s:.0f}s per worker, "
+                      f"rate = sum of per-worker step rates; wall incl. start-up {wall:.1f}s; "
+                      "AsyncVectorEnv stand-in (gymnasium absent)"}
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="config4", choices=sorted(WORKLOADS))
+    ap.add_argument("--envs-per-gpu", type=int, default=None)
+    ap.add_argument("--pool", type=int, default=None)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--validate", default="terminal")
+    ap.add_argument("--autoreset", default="same_step")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    cfg, n_env, pool_n, traceback, max_steps, desc = WORKLOADS[args.workload]
+    n_env = args.envs_per_gpu or n_env
+    pool_n = args.pool or pool_n
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        steps_rates = []
+        for _ in range(max(1, min(args.steps, 3))):        # each "step" = one bounded CPU sample
+            steps_rates.append(cpu_baseline(args.workload, budget_s=min(args.cpu_seconds, 10.0)))
+        best = max(steps_rates, key=lambda d: d["value"])
+        print(json.dumps({"impl": "reference", "metric": "env-steps/sec (whole box)", "value": best["value"],
+                          "unit": "env-steps/s", "n_gpus": 0, "steps": len(steps_rates), "warmup": 0,
+                          "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": "int32", "data": "synthetic",
+                          "config": {"workload": args.workload, "description": desc, "traceback": traceback,
+                                     "max_steps": max_steps},
+                          "cpu_baseline": best,
+                          "e2e": {"value": best["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0,
+                                  "d2h_bytes_per_step": 0}}))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from sparc_gym_b200.dataset import config_pool
+    from sparc_gym_b200.vec_env import SparcVecEnv
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    t_build = time.perf_counter()
+    rows = config_pool(cfg, n_puzzles=pool_n)
+    env = SparcVecEnv(rows, n_env, traceback=traceback, max_steps=max_steps, autoreset_mode=args.autoreset,
+                      puzzle_stride=1, validate=args.validate, device=dev)
+    st = env.store
+    t_build = time.perf_counter() - t_build
+    K, W = args.steps, args.warmup
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    actions = torch.randint(0, 4, (K + W, n_env), dtype=torch.uint8, device=dev, generator=gen)
+    env.reset()
+    for t in range(W):
+        env.step(actions[t])
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing: K steps, CUDA events on the launching stream
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    launches0 = env.kernel_launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for t in range(W, W + K):
+        env.step(actions[t])
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = env.kernel_launches - launches0
+    clocks = sampler.summary() if sampler else None
+    t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_max = float(t_ms.item())
+
+    # ---- end to end: host action buffer -> H2D -> step -> D2H reward/terminated/truncated, every step
+    e2e = None
+    if not args.no_e2e:
+        a_host = torch.randint(0, 4, (n_env,), dtype=torch.uint8).pin_memory()
+        r_host = torch.empty(n_env, dtype=torch.float32).pin_memory()
+        te_host = torch.empty(n_env, dtype=torch.uint8).pin_memory()
+        tr_host = torch.empty(n_env, dtype=torch.uint8).pin_memory()
+        for _ in range(3):
+            env.step_host(a_host, r_host, te_host, tr_host)
+        barrier()
+        t0 = time.perf_counter()
+        ev0.record()
+        for _ in range(K):
+            env.step_host(a_host, r_host, te_host, tr_host)
+        ev1.record()
+        barrier()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        e_ms = torch.tensor([max(ev0.elapsed_time(ev1), 0.0)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(e_ms, op=dist.ReduceOp.MAX)
+        e2e = {"value": round(n_env * world * K / (float(e_ms.item()) / 1e3), 1), "unit": "env-steps/s",
+               "h2d_bytes_per_step": n_env * world, "d2h_bytes_per_step": n_env * world * 6,
+               "wall_ms_per_step": round(wall_ms / K, 4),
+               "api": "SparcVecEnv.step_host -> sparc_step_host (pinned host actions in; reward f32 + terminated u8 + "
+                      "truncated u8 out; observation tensors stay on the device for the policy)"}
+
+    # ---- episode statistics: the only cross-GPU traffic (NCCL all-reduce of int64[8])
+    stats = env.stats().clone()
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+    stats = stats.cpu().tolist()
+
+    if rank == 0:
+        from sparc_gym_b200 import abi
+        peak, peak_src = measured_peaks()
+        b_alg = st.algorithmic_bytes_per_step()
+        value = n_env * world * K / (ms_max / 1e3)
+        kernel_ms = ms_max / max(launches, 1)
+        achieved = b_alg * n_env / (kernel_ms / 1e3) / 1e9
+        line = {
+            "metric": "env-steps/sec (whole box)", "value": round(value, 1), "unit": "env-steps/s",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": round(ms_max / K, 5),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
+            "data": "synthetic",
+            "config": {"workload": args.workload, "description": desc, "envs_per_gpu": n_env,
+                       "global_envs": n_env * world, "pool_puzzles": pool_n, "lattice": [st.slab_x, st.slab_y],
+                       "planes": st.plane_keys, "traceback": traceback, "max_steps": max_steps,
+                       "autoreset": args.autoreset, "validate": args.validate, "obs_mode": "full rewrite, reference dtypes",
+                       "l2": ("observation written per step (%.0f MB) exceeds L2 (126 MB)" % (b_alg * n_env / 1e6))
+                             if b_alg * n_env > 126e6 else
+                             ("observation per step (%.1f MB) fits in L2: writes may be absorbed by L2" % (b_alg * n_env / 1e6)),
+                       "parallelism": f"env-sharded x{world}, no data-path collective", "setup_s": round(t_build, 1)},
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                         "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                         "kernel": "k_env", "algorithmic_bytes_per_env_step": b_alg,
+                         "envs_per_launch": n_env, "kernel_ms": round(kernel_ms, 5)},
+            "episode_stats": dict(zip(abi.STAT_NAMES, stats)),
+        }
+        if not args.no_cpu_baseline and world == 1:
+            # fresh interpreter: the worker pool must not be forked from a process holding a CUDA context
+            res = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload",
+                                  args.workload, "--steps", "1", "--cpu-seconds", str(args.cpu_seconds)],
+                                 capture_output=True, text=True)
+            try:
+                line["cpu_baseline"] = json.loads(res.stdout.strip().splitlines()[-1])["cpu_baseline"]
+            except Exception:
+                line["cpu_baseline"] = {"value": None, "unit": "env-steps/s", "cores": os.cpu_count(), "kind": "port",
+                                        "sample": "failed: " + res.stderr[-300:]}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

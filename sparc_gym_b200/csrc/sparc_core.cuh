@@ -1,0 +1,700 @@
+// sparc_core.cuh -- per-env dynamics, rule validator and observation encoder of the batched
+// SPaRC environment.  Everything here is written against explicit (thread id, thread count)
+// arguments and a handful of wrapped intrinsics so that the *same source* compiles
+//   * with nvcc for sm_100a (the product: kernels in sparc_b200.cu), and
+//   * with g++ as plain C++ (tests/emu: a test-only harness that replays the kernels' logic on
+//     the CPU so that logic bugs are found without a GPU).  The product never uses that build.
+//
+// Reference being restated: SPaRC_Gym/SPaRC_Gym.py ("SG.py"); SURVEY.md Appendix A is the spec.
+#pragma once
+#include <stdint.h>
+#include "../../include/sparc_b200.h"
+
+#if defined(__CUDACC__)
+#define SPARC_HD __host__ __device__ __forceinline__
+#define SPARC_D __device__ __forceinline__
+#else
+#define SPARC_HD inline
+#define SPARC_D inline
+#endif
+
+// ---------------------------------------------------------------------------------------------
+// intrinsics (device versions map to single SASS instructions; host versions are for the emu)
+// ---------------------------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+SPARC_D uint32_t sp_brev(uint32_t v) { return __brev(v); }
+SPARC_D int sp_popc(uint32_t v) { return __popc(v); }
+SPARC_D int sp_popcll(uint64_t v) { return __popcll(v); }
+SPARC_D int sp_ffs(uint32_t v) { return __ffs(v); }
+SPARC_D int sp_ffsll(uint64_t v) { return __ffsll((long long)v); }
+SPARC_D uint32_t sp_funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) { return __funnelshift_r(lo, hi, sh); }
+template <typename T> SPARC_D T sp_ldg(const T* p) { return __ldg(p); }
+struct sp_u4 { uint32_t x, y, z, w; };
+SPARC_D sp_u4 sp_ldg4(const uint32_t* p) { uint4 v = __ldg(reinterpret_cast<const uint4*>(p)); return {v.x, v.y, v.z, v.w}; }
+// streaming 128-bit store: the observation is written once and not re-read by this kernel
+SPARC_D void sp_st4(int32_t* p, int32_t a, int32_t b, int32_t c, int32_t d) {
+    asm volatile("st.global.cs.v4.s32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+#else
+SPARC_HD uint32_t sp_brev(uint32_t v) {
+    v = ((v >> 1) & 0x55555555u) | ((v & 0x55555555u) << 1);
+    v = ((v >> 2) & 0x33333333u) | ((v & 0x33333333u) << 2);
+    v = ((v >> 4) & 0x0F0F0F0Fu) | ((v & 0x0F0F0F0Fu) << 4);
+    v = ((v >> 8) & 0x00FF00FFu) | ((v & 0x00FF00FFu) << 8);
+    return (v >> 16) | (v << 16);
+}
+SPARC_HD int sp_popc(uint32_t v) { return __builtin_popcount(v); }
+SPARC_HD int sp_popcll(uint64_t v) { return __builtin_popcountll(v); }
+SPARC_HD int sp_ffs(uint32_t v) { return __builtin_ffs((int)v); }
+SPARC_HD int sp_ffsll(uint64_t v) { return __builtin_ffsll((long long)v); }
+SPARC_HD uint32_t sp_funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) {
+    sh &= 31; return sh ? (lo >> sh) | (hi << (32 - sh)) : lo;
+}
+template <typename T> SPARC_HD T sp_ldg(const T* p) { return *p; }
+struct sp_u4 { uint32_t x, y, z, w; };
+SPARC_HD sp_u4 sp_ldg4(const uint32_t* p) { return {p[0], p[1], p[2], p[3]}; }
+SPARC_HD void sp_st4(int32_t* p, int32_t a, int32_t b, int32_t c, int32_t d) { p[0] = a; p[1] = b; p[2] = c; p[3] = d; }
+#endif
+
+// ---------------------------------------------------------------------------------------------
+// device-side views
+// ---------------------------------------------------------------------------------------------
+struct StoreDev {
+    int n_puzzles, SX, SY, S;      // slab lattice, S = SX*SY nodes
+    int P, L, W, Wpad;             // planes, L = P*S bits per env, W words, padded (odd, >= 9) row stride
+    int nv;                        // words of one dense plane: ceil(S/32)
+    const SparcPuzzleHeader* hdr;
+    const uint32_t* nb;            // [n][SPARC_N_NODE_BOARDS][8]
+    const uint64_t* cb;            // [n][SPARC_N_CELL_BOARDS]
+    const uint32_t* sbits;         // [n][W]
+    const uint8_t* color;          // [n][S]
+    const int32_t* info;           // [n][S]
+    const SparcShape* shapes;
+    const uint32_t* trie;          // [nodes][8]
+};
+
+// per-env state, struct of arrays over envs (coalesced: consecutive lanes = consecutive envs)
+struct StateDev {
+    uint32_t* core;                // [N][4]: puzzle, step, trie node, x | y<<8 | on_depth<<16 | flags<<24
+    uint32_t* vis;                 // [8][N]: visited plane, dense slab order (== set of path nodes)
+    int32_t* ep_ret;               // [N]: episode return in cents
+    uint32_t* moves;               // [12][N]: stack of 2-bit moves (traceback only), else nullptr
+    unsigned long long* stats;     // [SPARC_N_STATS]
+};
+
+enum { FL_DONE = 1, FL_TERM = 2, FL_TRUNC = 4 };
+#define SPARC_MOVE_WORDS 12
+
+struct EnvRegs {                   // one env's state in registers
+    uint32_t puzzle, step, tnode;
+    int x, y, on_depth, flags;
+    uint32_t v[8];
+    int ep_ret;
+};
+
+struct StepCfg {
+    long long n_envs;
+    int traceback, max_steps, autoreset, stride, validate_mode;
+};
+
+struct StepResult {
+    int reward_code, terminated, truncated, legal_mask, rule_flags;
+    int stat_done, stat_stepped;   // for the statistics reduction
+    int final_step, final_ret, final_win;
+};
+
+SPARC_HD uint32_t board_word(const uint32_t (&b)[8], int k) {
+    uint32_t r = b[0];
+    r = (k == 1) ? b[1] : r; r = (k == 2) ? b[2] : r; r = (k == 3) ? b[3] : r; r = (k == 4) ? b[4] : r;
+    r = (k == 5) ? b[5] : r; r = (k == 6) ? b[6] : r; r = (k == 7) ? b[7] : r;
+    return r;
+}
+SPARC_HD int board_bit(const uint32_t (&b)[8], int n) { return (board_word(b, n >> 5) >> (n & 31)) & 1; }
+SPARC_HD void board_flip(uint32_t (&b)[8], int n) {
+    const uint32_t m = 1u << (n & 31);
+    const int k = n >> 5;
+#pragma unroll
+    for (int i = 0; i < 8; i++) b[i] ^= (i == k) ? m : 0u;
+}
+SPARC_HD int board_popc(const uint32_t (&b)[8]) {
+    int c = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) c += sp_popc(b[i]);
+    return c;
+}
+SPARC_HD void load_board(uint32_t (&b)[8], const uint32_t* p) {
+    sp_u4 a = sp_ldg4(p), c = sp_ldg4(p + 4);
+    b[0] = a.x; b[1] = a.y; b[2] = a.z; b[3] = a.w; b[4] = c.x; b[5] = c.y; b[6] = c.z; b[7] = c.w;
+}
+
+struct HdrRegs { int X, Y, sx, sy, tx, ty, n_shapes, flags; uint32_t shape_off, trie_root; };
+SPARC_HD HdrRegs load_hdr(const StoreDev& st, uint32_t puzzle) {
+    sp_u4 a = sp_ldg4(reinterpret_cast<const uint32_t*>(st.hdr + puzzle));
+    HdrRegs h;
+    h.X = a.x & 0xff; h.Y = (a.x >> 8) & 0xff; h.sx = (a.x >> 16) & 0xff; h.sy = a.x >> 24;
+    h.tx = a.y & 0xff; h.ty = (a.y >> 8) & 0xff; h.n_shapes = (a.y >> 16) & 0xff; h.flags = a.y >> 24;
+    h.shape_off = a.z; h.trie_root = a.w;
+    return h;
+}
+
+// action id -> (dx, dy): right, up, left, down on [x, y] (SG.py:12-25, 212-217)
+SPARC_HD int dir_dx(int a) { return (a == 0) - (a == 2); }
+SPARC_HD int dir_dy(int a) { return (a == 3) - (a == 1); }
+
+// ---------------------------------------------------------------------------------------------
+// state load / store
+// ---------------------------------------------------------------------------------------------
+SPARC_HD void load_env(EnvRegs& e, const StateDev& sd, const StoreDev& st, long long n, long long i) {
+    const uint32_t* c = sd.core + 4 * i;
+#if defined(__CUDA_ARCH__)
+    uint4 q = *reinterpret_cast<const uint4*>(c);
+    e.puzzle = q.x; e.step = q.y; e.tnode = q.z; uint32_t w = q.w;
+#else
+    e.puzzle = c[0]; e.step = c[1]; e.tnode = c[2]; uint32_t w = c[3];
+#endif
+    e.x = w & 0xff; e.y = (w >> 8) & 0xff; e.on_depth = (w >> 16) & 0xff; e.flags = w >> 24;
+#pragma unroll
+    for (int k = 0; k < 8; k++) e.v[k] = (k < st.nv) ? sd.vis[(long long)k * n + i] : 0u;
+    e.ep_ret = sd.ep_ret[i];
+}
+SPARC_HD void store_env(const EnvRegs& e, const StateDev& sd, const StoreDev& st, long long n, long long i) {
+    uint32_t* c = sd.core + 4 * i;
+    const uint32_t w = (uint32_t)e.x | ((uint32_t)e.y << 8) | ((uint32_t)e.on_depth << 16) | ((uint32_t)e.flags << 24);
+#if defined(__CUDA_ARCH__)
+    *reinterpret_cast<uint4*>(c) = make_uint4(e.puzzle, e.step, e.tnode, w);
+#else
+    c[0] = e.puzzle; c[1] = e.step; c[2] = e.tnode; c[3] = w;
+#endif
+#pragma unroll
+    for (int k = 0; k < 8; k++) if (k < st.nv) sd.vis[(long long)k * n + i] = e.v[k];
+    sd.ep_ret[i] = e.ep_ret;
+}
+
+// clean reset (SG.py:1092-1095, 173-187; SURVEY Q1 neutralised)
+SPARC_HD void env_reset(EnvRegs& e, const StoreDev& st, uint32_t puzzle) {
+    const HdrRegs h = load_hdr(st, puzzle);
+    e.puzzle = puzzle; e.step = 0; e.x = h.sx; e.y = h.sy; e.flags = 0; e.ep_ret = 0;
+    e.tnode = h.trie_root; e.on_depth = h.trie_root ? 1 : 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) e.v[k] = 0;
+    board_flip(e.v, h.sx * st.SY + h.sy);
+}
+
+// ---------------------------------------------------------------------------------------------
+// dynamics (SG.py:1024-1051 legality, 1111-1223 step)
+// ---------------------------------------------------------------------------------------------
+// bit a of the result: action a is legal from (x, y); (px, py) = path[-2] or (-1,-1)
+SPARC_HD int legal_actions(const StoreDev& st, const uint32_t (&walk)[8], const uint32_t (&v)[8],
+                           int x, int y, int px, int py) {
+    int mask = 0;
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+        const int nx = x + dir_dx(a), ny = y + dir_dy(a);
+        if ((unsigned)nx >= (unsigned)st.SX || (unsigned)ny >= (unsigned)st.SY) continue;
+        const int n = nx * st.SY + ny;
+        if (!board_bit(walk, n)) continue;                 // out of this puzzle's lattice, or a gap
+        const int fresh = !board_bit(v, n);
+        if (fresh || (nx == px && ny == py)) mask |= 1 << a;
+    }
+    return mask;
+}
+
+// top of the move stack = the move that led to path[-1]; path length = plen
+SPARC_HD int stack_top(const StateDev& sd, long long n, long long i, int plen) {
+    const int idx = plen - 2;
+    return (sd.moves[(long long)(idx >> 4) * n + i] >> ((idx & 15) * 2)) & 3;
+}
+
+SPARC_HD void env_step(EnvRegs& e, const StoreDev& st, const StateDev& sd, const StepCfg& cfg, long long i,
+                       long long action, StepResult& r) {
+    const HdrRegs h = load_hdr(st, e.puzzle);
+    uint32_t walk[8];
+    load_board(walk, st.nb + ((size_t)e.puzzle * SPARC_N_NODE_BOARDS + SPARC_NB_WALK) * 8);
+    int plen = board_popc(e.v);                            // path nodes are distinct, visited == set(path)
+    const int tb = cfg.traceback && sd.moves != nullptr;
+    int px = -1, py = -1;
+    if (tb && plen >= 2) { const int d = stack_top(sd, cfg.n_envs, i, plen); px = e.x - dir_dx(d); py = e.y - dir_dy(d); }
+
+    e.step += 1;                                           // SG.py:1132 (illegal actions count too)
+    int truncated = (int)e.step >= cfg.max_steps;          // SG.py:1134
+    int moved = 0;
+    const int legal_now = legal_actions(st, walk, e.v, e.x, e.y, px, py);
+    if (action >= 0 && action < 4 && ((legal_now >> (int)action) & 1)) {
+        const int a = (int)action;
+        const int nx = e.x + dir_dx(a), ny = e.y + dir_dy(a);
+        const int n = nx * st.SY + ny;
+        if (board_bit(e.v, n)) {                           // traceback undo (SG.py:1141-1166)
+            board_flip(e.v, e.x * st.SY + e.y);
+            if (e.on_depth == plen) {                      // cursor leaves the popped node
+                e.tnode = sp_ldg(st.trie + (size_t)e.tnode * SPARC_TRIE_NODE_WORDS + 4);
+                e.on_depth = plen - 1;
+            }
+            plen -= 1;
+            px = -1; py = -1;
+            if (plen >= 2) { const int d = stack_top(sd, cfg.n_envs, i, plen); px = nx - dir_dx(d); py = ny - dir_dy(d); }
+        } else {                                           // fresh node (SG.py:1167-1188)
+            board_flip(e.v, n);
+            if (e.on_depth == plen) {
+                const uint32_t child = sp_ldg(st.trie + (size_t)e.tnode * SPARC_TRIE_NODE_WORDS + a);
+                if (child) { e.tnode = child; e.on_depth = plen + 1; }
+            }
+            if (tb) {                                      // push the move
+                const int idx = plen - 1;
+                uint32_t* wp = sd.moves + (long long)(idx >> 4) * cfg.n_envs + i;
+                const int sh = (idx & 15) * 2;
+                *wp = (*wp & ~(3u << sh)) | ((uint32_t)a << sh);
+            }
+            plen += 1;
+            px = e.x; py = e.y;
+            if (!tb) { px = -1; py = -1; }
+        }
+        e.x = nx; e.y = ny;
+        moved = 1;
+    }
+    const int terminated = (e.x == h.tx && e.y == h.ty);   // SG.py:1192
+    const int legal_after = legal_actions(st, walk, e.v, e.x, e.y, px, py);
+    if (legal_after == 0) truncated = 1;                   // SG.py:1195-1196
+    if (terminated) truncated = 0;                         // SG.py:1198-1199
+    const int on_trie = (e.on_depth == plen) && e.tnode != 0;
+    int code = SPARC_R_ZERO;
+    if (terminated || truncated) {                         // SG.py:1204-1213
+        const int is_end = on_trie ? (int)sp_ldg(st.trie + (size_t)e.tnode * SPARC_TRIE_NODE_WORDS + 5) : 0;
+        code = is_end ? SPARC_R_WIN : SPARC_R_LOSE;
+    } else if (moved && (h.flags & 1)) {                   // SG.py:1214-1223
+        code = on_trie ? SPARC_R_ON_PATH : SPARC_R_OFF_PATH;
+    }
+    e.ep_ret += (code == SPARC_R_ON_PATH) - (code == SPARC_R_OFF_PATH) + 100 * ((code == SPARC_R_WIN) - (code == SPARC_R_LOSE));
+    r.reward_code = code; r.terminated = terminated; r.truncated = truncated; r.legal_mask = legal_after;
+}
+
+// legal mask of the current state without stepping (reset / frozen envs)
+SPARC_HD int env_legal_now(const EnvRegs& e, const StoreDev& st, const StateDev& sd, const StepCfg& cfg, long long i) {
+    uint32_t walk[8];
+    load_board(walk, st.nb + ((size_t)e.puzzle * SPARC_N_NODE_BOARDS + SPARC_NB_WALK) * 8);
+    const int plen = board_popc(e.v);
+    int px = -1, py = -1;
+    if (cfg.traceback && sd.moves != nullptr && plen >= 2) {
+        const int d = stack_top(sd, cfg.n_envs, i, plen); px = e.x - dir_dx(d); py = e.y - dir_dy(d);
+    }
+    return legal_actions(st, walk, e.v, e.x, e.y, px, py);
+}
+
+// ---------------------------------------------------------------------------------------------
+// rule validator (SG.py:374-950) on 16-stride node boards and uint64 rule-cell boards
+// ---------------------------------------------------------------------------------------------
+// fill f (subset of p) along y inside every 16-bit row of the word; p has bits 15 and 31 clear
+SPARC_HD uint32_t row_fill(uint32_t p, uint32_t f) {
+    const uint32_t up = ((p ^ (p + f)) & p) | f;
+    const uint32_t pr = sp_brev(p), fr = sp_brev(up);
+    const uint32_t dn = ((pr ^ (pr + fr)) & pr) | fr;
+    return sp_brev(dn);
+}
+
+struct Cnt3 { uint64_t c0, c1, c2; };                      // bit-sliced per-cell demand counters (0..7)
+SPARC_HD void cnt_add(Cnt3& c, uint64_t m) { uint64_t t = c.c0 & m; c.c0 ^= m; m = t; t = c.c1 & m; c.c1 ^= m; c.c2 ^= t; }
+SPARC_HD void cnt_sub(Cnt3& c, uint64_t m) { uint64_t t = ~c.c0 & m; c.c0 ^= m; m = t; t = ~c.c1 & m; c.c1 ^= m; c.c2 ^= t; }
+
+SPARC_HD uint64_t shape_place(const SparcShape& s, int cx, int cy, int w, int h) {
+    if (s.flags) return 0;                                  // unplaceable / empty
+    const int y0 = cy - (int)s.anchor_dy;
+    if (y0 < 0 || cx + (int)s.max_dx >= w || y0 + (int)s.span_y >= h) return 0;   // SG.py:880-883
+    return s.mask << (cx * 8 + y0);
+}
+
+// exact-fit existence (SG.py:738-895): ylops first (any rule-cell anchor, may leave the region,
+// may stack), then polys anchored at the first still-demanded cell.  n_poly / n_ylop: instances
+// per shape slot inside this region.
+SPARC_HD bool exact_fit(uint64_t region, int w, int h, const SparcShape* shapes, int ns,
+                        const uint8_t* n_poly, const uint8_t* n_ylop) {
+    uint8_t rem[SPARC_MAX_SHAPES];
+    uint8_t ylist[SPARC_MAX_YLOPS];
+    uint8_t fr_item[64], fr_pos[64];
+    int ny = 0;
+    for (int s = 0; s < ns; s++) {
+        const int empty = (shapes[s].flags & 2) != 0;       // zero-area shapes never touch the grid
+        rem[s] = empty ? 0 : n_poly[s];
+        for (int k = 0; k < (empty ? 0 : (int)n_ylop[s]); k++) if (ny < SPARC_MAX_YLOPS) ylist[ny++] = (uint8_t)s;
+    }
+    Cnt3 c = {region, 0, 0};
+    int level = 0, it = 0;
+    for (;;) {
+        bool found = false;
+        if (level < ny) {                                   // SG.py:794-816
+            const SparcShape& sh = shapes[ylist[level]];
+            for (int a = it; a < 64; a++) {
+                const int cx = a >> 3, cy = a & 7;
+                if (cx >= w || cy >= h) continue;
+                const uint64_t m = shape_place(sh, cx, cy, w, h);
+                if (!m) continue;
+                cnt_add(c, m); fr_pos[level] = (uint8_t)a; level++; it = 0; found = true; break;
+            }
+        } else {                                            // SG.py:818-853
+            const uint64_t nz = c.c0 | c.c1 | c.c2;
+            if (nz == 0) return true;
+            const int t = sp_ffsll(nz) - 1;
+            for (int s = it; s < ns; s++) {
+                if (!rem[s]) continue;
+                const uint64_t m = shape_place(shapes[s], t >> 3, t & 7, w, h);
+                if (!m || (m & ~nz)) continue;              // a covered cell would go positive (SG.py:822)
+                cnt_sub(c, m); rem[s]--; fr_item[level] = (uint8_t)s; fr_pos[level] = (uint8_t)t;
+                level++; it = 0; found = true; break;
+            }
+        }
+        if (found) continue;
+        if (level == 0) return false;
+        level--;                                            // backtrack
+        if (level < ny) {
+            const int a = fr_pos[level];
+            cnt_sub(c, shape_place(shapes[ylist[level]], a >> 3, a & 7, w, h));
+            it = a + 1;
+        } else {
+            const int s = fr_item[level], t = fr_pos[level];
+            cnt_add(c, shape_place(shapes[s], t >> 3, t & 7, w, h)); rem[s]++;
+            it = s + 1;
+        }
+    }
+}
+
+// vd: the env's visited plane in dense slab order, 9 readable words (word 8 may be anything
+// when S <= 256).  region_map: optional int8[SX*SY] (row-major x, y), pre-filled with -1.
+SPARC_HD int validate_env(const StoreDev& st, uint32_t puzzle, const uint32_t* vd, int ax, int ay,
+                          int8_t* region_map) {
+    const HdrRegs h = load_hdr(st, puzzle);
+    const uint32_t* nbp = st.nb + (size_t)puzzle * SPARC_N_NODE_BOARDS * 8;
+    // visited: dense -> 16-stride
+    uint32_t V[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) V[k] = 0;
+    const uint32_t rowmask = (1u << st.SY) - 1u;
+    for (int x = 0; x < st.SX; x++) {
+        const int pos = x * st.SY;
+        const uint32_t row = sp_funnel_r(vd[pos >> 5], vd[(pos >> 5) + 1], pos & 31) & rowmask;
+        const uint32_t sh = row << ((x & 1) * 16);
+#pragma unroll
+        for (int k = 0; k < 8; k++) V[k] |= (k == (x >> 1)) ? sh : 0u;
+    }
+    uint32_t G[8], C[8], VAL[8], T[8];
+    load_board(G, nbp + SPARC_NB_GAPS16 * 8);
+    load_board(C, nbp + SPARC_NB_CELL16 * 8);
+    load_board(VAL, nbp + SPARC_NB_VALID16 * 8);
+    int flags = 0;
+    if (ax == h.tx && ay == h.ty) flags |= SPARC_RULE_REACHED_TARGET;            // SG.py:488
+    flags |= SPARC_RULE_PATH_NOT_CROSSING;      // path nodes are distinct by construction (SG.py:498)
+    {                                                                           // SG.py:508, 521
+        uint32_t gv = 0, dm = 0;
+        load_board(T, nbp + SPARC_NB_DOT16 * 8);
+#pragma unroll
+        for (int k = 0; k < 8; k++) { gv |= G[k] & V[k]; dm |= T[k] & ~V[k]; }
+        if (!gv) flags |= SPARC_RULE_NO_GAP_VIOLATIONS;
+        if (!dm) flags |= SPARC_RULE_ALL_DOTS;
+    }
+    {   // triangles (SG.py:617-646): number of the 4 neighbour nodes on the path == count
+        uint32_t bad = 0;
+        uint32_t T1[8], T2[8], T3[8], T4[8];
+        load_board(T1, nbp + SPARC_NB_TRI1 * 8); load_board(T2, nbp + SPARC_NB_TRI2 * 8);
+        load_board(T3, nbp + SPARC_NB_TRI3 * 8); load_board(T4, nbp + SPARC_NB_TRI4 * 8);
+        load_board(T, nbp + SPARC_NB_TRIBAD * 8);
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const uint32_t a = (V[k] << 16) | (k > 0 ? V[k - 1] >> 16 : 0u);   // node (x-1, y)
+            const uint32_t b = (V[k] >> 16) | (k < 7 ? V[k + 1] << 16 : 0u);   // node (x+1, y)
+            const uint32_t c = (V[k] << 1) & 0xFFFEFFFEu;                      // node (x, y-1)
+            const uint32_t d = (V[k] >> 1) & 0x7FFF7FFFu;                      // node (x, y+1)
+            const uint32_t s1 = a ^ b, c1 = a & b, s2 = c ^ d, c2 = c & d;
+            const uint32_t b0 = s1 ^ s2, cr = s1 & s2, b1 = c1 ^ c2 ^ cr, b2 = c1 & c2;
+            const uint32_t eq1 = b0 & ~b1 & ~b2, eq2 = ~b0 & b1 & ~b2, eq3 = b0 & b1, eq4 = b2;
+            bad |= (T1[k] & ~eq1) | (T2[k] & ~eq2) | (T3[k] & ~eq3) | (T4[k] & ~eq4) | T[k];
+        }
+        if (!bad) flags |= SPARC_RULE_TRIANGLES;
+    }
+    // regions (SG.py:422-454): passable = rule cell, or neither gap nor path (Q6)
+    uint32_t Pm[8], unl[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) { Pm[k] = VAL[k] & (C[k] | ~(G[k] | V[k])); unl[k] = C[k]; }
+    const uint64_t* cbp = st.cb + (size_t)puzzle * SPARC_N_CELL_BOARDS;
+    const uint64_t STAR = sp_ldg(cbp + SPARC_CB_STAR), SQ = sp_ldg(cbp + SPARC_CB_SQUARE);
+    const uint64_t SB0 = sp_ldg(cbp + SPARC_CB_SYM1), SB1 = sp_ldg(cbp + SPARC_CB_SYM2);
+    uint64_t COL[8], anycol = 0;
+#pragma unroll
+    for (int c = 0; c < 8; c++) { COL[c] = sp_ldg(cbp + SPARC_CB_COLOR1 + c); anycol |= COL[c]; }
+    const SparcShape* shapes = st.shapes + h.shape_off;
+    const int w = (h.X - 1) >> 1, hh = (h.Y - 1) >> 1;
+    bool sq_ok = true, star_ok = true, poly_ok = true;
+    int rid = 0;
+    for (;;) {
+        int k0 = -1;
+#pragma unroll
+        for (int k = 7; k >= 0; k--) k0 = unl[k] ? k : k0;
+        if (k0 < 0) break;
+        uint32_t f[8];
+        const uint32_t seed = board_word(unl, k0) & (0u - board_word(unl, k0));    // lowest set bit: raster order
+#pragma unroll
+        for (int k = 0; k < 8; k++) f[k] = (k == k0) ? seed : 0u;
+        for (;;) {                                                              // flood to fix-point
+            uint32_t g[8], ch = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) g[k] = row_fill(Pm[k], f[k]);
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const uint32_t up = (g[k] << 16) | (k > 0 ? g[k - 1] >> 16 : 0u);
+                const uint32_t dn = (g[k] >> 16) | (k < 7 ? g[k + 1] << 16 : 0u);
+                const uint32_t nw = (g[k] | up | dn) & Pm[k];
+                ch |= nw ^ f[k];
+                f[k] = nw;
+            }
+            if (!ch) break;
+        }
+        uint64_t R = 0;                                     // component -> rule-cell board
+#pragma unroll
+        for (int cx = 0; cx < 7; cx++) {
+            const uint32_t cells = f[cx] & C[cx];
+            unl[cx] &= ~cells;
+            uint32_t t = (cells >> 17) & 0x5555u;           // x = 2cx+1 is the high half; y odd -> even slots
+            t = (t | (t >> 1)) & 0x3333u; t = (t | (t >> 2)) & 0x0F0Fu; t = (t | (t >> 4)) & 0x00FFu;
+            R |= (uint64_t)t << (cx * 8);
+        }
+        unl[7] &= ~(f[7] & C[7]);
+        if (region_map) {
+            uint64_t m = R;
+            while (m) { const int b = sp_ffsll(m) - 1; m &= m - 1; region_map[(2 * (b >> 3) + 1) * st.SY + 2 * (b & 7) + 1] = (int8_t)rid; }
+        }
+        // squares (SG.py:534-552): at most one distinct non-zero colour per region
+        const uint64_t sq = SQ & R;
+        if (sq) {
+            int nc = 0;
+#pragma unroll
+            for (int c = 0; c < 8; c++) nc += (sq & COL[c]) != 0;
+            if (nc > 1) sq_ok = false;
+        }
+        // stars (SG.py:554-614): every star colour must total exactly 2 symbols in the region
+        const uint64_t sr = STAR & R;
+        if (sr) {
+            if (sr & ~anycol) star_ok = false;              // colourless star (SG.py:580-582)
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                if (sr & COL[c]) {
+                    const uint64_t rc = R & COL[c];
+                    if (sp_popcll(SB0 & rc) + 2 * sp_popcll(SB1 & rc) != 2) star_ok = false;
+                }
+            }
+        }
+        // polys / ylops (SG.py:648-710)
+        if (h.n_shapes && poly_ok) {
+            uint8_t np[SPARC_MAX_SHAPES], nyl[SPARC_MAX_SHAPES];
+            int net = 0, any = 0;
+            for (int s = 0; s < h.n_shapes; s++) {
+                const int a = sp_popcll(sp_ldg(&shapes[s].poly_cells) & R), b = sp_popcll(sp_ldg(&shapes[s].ylop_cells) & R);
+                np[s] = (uint8_t)a; nyl[s] = (uint8_t)b; any |= a | b;
+                net += (a - b) * (int)shapes[s].area;
+            }
+            if (any) {
+                if (net != sp_popcll(R)) poly_ok = false;   // SG.py:679-682
+                else if (!exact_fit(R, w, hh, shapes, h.n_shapes, np, nyl)) poly_ok = false;
+            }
+        }
+        rid++;
+    }
+    if (sq_ok) flags |= SPARC_RULE_SQUARES;
+    if (star_ok) flags |= SPARC_RULE_STARS;
+    if (poly_ok) flags |= SPARC_RULE_POLY_YLOP;
+    if ((flags & 0xFF) == 0xFF) flags |= SPARC_RULE_ALL;                        // SG.py:932-935
+    return flags;
+}
+
+// ---------------------------------------------------------------------------------------------
+// observation encoder (SG.py:956-979 with a full rewrite in the reference dtypes)
+//   rows : shared staging, one row of Wpad words per env of the tile = the env's P one-hot
+//          planes bit-packed in output order
+//   tile : nE consecutive envs starting at env0 (env0 % 4 == 0 keeps every stream 16-B aligned)
+// ---------------------------------------------------------------------------------------------
+// stage 1 (cooperative): static planes of each env's puzzle -> rows
+SPARC_HD void stage_static(const StoreDev& st, uint32_t* rows, const uint32_t* tile_puzzle, int nE, int tid, int nthr) {
+    const int total = nE * st.W;
+    for (int idx = tid; idx < total; idx += nthr) {
+        const int j = idx / st.W, k = idx - j * st.W;
+        rows[j * st.Wpad + k] = sp_ldg(st.sbits + (size_t)tile_puzzle[j] * st.W + k);
+    }
+}
+// stage 2 (owner thread of env j): OR in the dynamic planes: visited = plane 0, agent = plane 2
+SPARC_HD void stage_dynamic(const StoreDev& st, uint32_t* rows, int j, const EnvRegs& e) {
+    uint32_t* row = rows + j * st.Wpad;
+#pragma unroll
+    for (int k = 0; k < 8; k++) if (k < st.nv) row[k] |= e.v[k];
+    const int ab = 2 * st.S + e.x * st.SY + e.y;
+    row[ab >> 5] |= 1u << (ab & 31);
+}
+// stage 3 (cooperative): expand bits to int32, 16 bytes per store, consecutive threads ->
+// consecutive 16-byte chunks of the tile's contiguous [nE][P][SX][SY] block
+SPARC_HD void expand_base(const StoreDev& st, const uint32_t* rows, int32_t* out_tile, int nE, int tid, int nthr) {
+    const int L = st.L;
+    const int total = nE * L;
+    const int nchunks = total >> 2;
+    int e0 = tid * 4;
+    int j = e0 / L, r0 = e0 - j * L;
+    const int adv = nthr * 4;
+    for (int c = tid; c < nchunks; c += nthr) {
+        uint32_t nib;
+        if (r0 + 3 < L) {
+            const uint32_t* rp = rows + j * st.Wpad + (r0 >> 5);
+            nib = sp_funnel_r(rp[0], rp[1], r0 & 31);
+        } else {                                            // chunk straddles two envs
+            nib = 0;
+            for (int q = 0; q < 4; q++) {
+                int rr = r0 + q, jj = j;
+                if (rr >= L) { rr -= L; jj++; }
+                nib |= ((rows[jj * st.Wpad + (rr >> 5)] >> (rr & 31)) & 1u) << q;
+            }
+        }
+        sp_st4(out_tile + 4 * (size_t)c, nib & 1, (nib >> 1) & 1, (nib >> 2) & 1, (nib >> 3) & 1);
+        r0 += adv;
+        while (r0 >= L) { r0 -= L; j++; }
+    }
+    for (int e = (nchunks << 2) + tid; e < total; e += nthr) {       // tail (< 4 elements)
+        const int jj = e / L, rr = e - jj * L;
+        out_tile[e] = (rows[jj * st.Wpad + (rr >> 5)] >> (rr & 31)) & 1u;
+    }
+}
+// colour plane: uint8 store -> int32 output
+SPARC_HD void expand_color(const StoreDev& st, const uint32_t* tile_puzzle, int32_t* out_tile, int nE, int tid, int nthr) {
+    const int S = st.S, total = nE * S, nchunks = total >> 2;
+    int e0 = tid * 4;
+    int j = e0 / S, r0 = e0 - j * S;
+    const int adv = nthr * 4;
+    for (int c = tid; c < nchunks; c += nthr) {
+        int32_t v[4];
+        int jj = j, rr = r0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            v[q] = sp_ldg(st.color + (size_t)tile_puzzle[jj] * S + rr);
+            if (++rr >= S) { rr = 0; jj++; if (jj >= nE) jj = nE - 1; }
+        }
+        sp_st4(out_tile + 4 * (size_t)c, v[0], v[1], v[2], v[3]);
+        r0 += adv;
+        while (r0 >= S) { r0 -= S; j++; }
+    }
+    for (int e = (nchunks << 2) + tid; e < total; e += nthr) {
+        const int jj = e / S, rr = e - jj * S;
+        out_tile[e] = sp_ldg(st.color + (size_t)tile_puzzle[jj] * S + rr);
+    }
+}
+// additional_info plane: int32 store -> int64 output (two elements per 16-byte store)
+SPARC_HD void expand_info(const StoreDev& st, const uint32_t* tile_puzzle, int64_t* out_tile, int nE, int tid, int nthr) {
+    const int S = st.S, total = nE * S, nchunks = total >> 1;
+    int e0 = tid * 2;
+    int j = e0 / S, r0 = e0 - j * S;
+    const int adv = nthr * 2;
+    for (int c = tid; c < nchunks; c += nthr) {
+        const int32_t a = sp_ldg(st.info + (size_t)tile_puzzle[j] * S + r0);
+        int jj = j, rr = r0 + 1;
+        if (rr >= S) { rr = 0; jj++; }
+        const int32_t b = sp_ldg(st.info + (size_t)tile_puzzle[jj] * S + rr);
+        sp_st4(reinterpret_cast<int32_t*>(out_tile + 2 * (size_t)c), a, a >> 31, b, b >> 31);
+        r0 += adv;
+        while (r0 >= S) { r0 -= S; j++; }
+    }
+    if ((total & 1) && tid == 0) {
+        const int e = total - 1, jj = e / S, rr = e - jj * S;
+        out_tile[e] = sp_ldg(st.info + (size_t)tile_puzzle[jj] * S + rr);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// one launch = reset or step of all envs (+ observation rewrite)
+// ---------------------------------------------------------------------------------------------
+struct KParams {
+    StoreDev st;
+    StateDev sd;
+    StepCfg cfg;
+    int mode;                // 0 = step, 1 = reset
+    int tile;                // envs per CTA
+    const void* actions;
+    int act_dtype;
+    const int32_t* reset_idx;
+    const uint8_t* reset_mask;
+    SparcStepOut out;
+    SparcObsOut obs;
+};
+
+SPARC_HD long long load_action(const void* p, int dtype, long long i) {
+    if (dtype == SPARC_ACT_U8) return reinterpret_cast<const uint8_t*>(p)[i];
+    if (dtype == SPARC_ACT_I32) return reinterpret_cast<const int32_t*>(p)[i];
+    return reinterpret_cast<const long long*>(p)[i];
+}
+
+SPARC_HD float reward_value(int code) {
+    return code == SPARC_R_ON_PATH ? 0.01f : code == SPARC_R_OFF_PATH ? -0.01f
+         : code == SPARC_R_WIN ? 1.0f : code == SPARC_R_LOSE ? -1.0f : 0.0f;
+}
+
+// Phase A for env i (one thread): reset / autoreset / frozen / live step, terminal validation,
+// per-env outputs.  `scratch` = 9 words the validator may use.  Returns true when `stats`
+// (SPARC_N_STATS counters) were filled.  On exit `e` is the state the observation must show.
+SPARC_HD bool phase_a(const KParams& p, long long i, EnvRegs& e, uint32_t* scratch, unsigned long long* stats) {
+    const StoreDev& st = p.st;
+    const long long n = p.cfg.n_envs;
+    load_env(e, p.sd, st, n, i);
+    StepResult r;
+    r.reward_code = SPARC_R_ZERO; r.terminated = 0; r.truncated = 0; r.legal_mask = 0; r.rule_flags = 0;
+    bool need_legal = false, have_stats = false;
+    if (p.mode == 1) {                                                   // ---- reset (SG.py:1057-1108)
+        const bool sel = p.reset_mask ? p.reset_mask[i] != 0 : true;
+        if (sel) {
+            uint32_t pz = p.reset_idx ? (uint32_t)p.reset_idx[i] : e.puzzle;
+            if (pz >= (uint32_t)st.n_puzzles) pz %= (uint32_t)st.n_puzzles;
+            env_reset(e, st, pz);
+            store_env(e, p.sd, st, n, i);
+        }
+        need_legal = true;
+        r.terminated = (e.flags & FL_TERM) != 0; r.truncated = (e.flags & FL_TRUNC) != 0;
+    } else if (e.flags & FL_DONE) {                                      // ---- finished episode
+        if (p.cfg.autoreset == SPARC_AUTORESET_NEXT_STEP) {
+            env_reset(e, st, (e.puzzle + (uint32_t)p.cfg.stride) % (uint32_t)st.n_puzzles);
+            store_env(e, p.sd, st, n, i);
+        } else {                                                         // frozen until sparc_reset
+            r.terminated = (e.flags & FL_TERM) != 0; r.truncated = (e.flags & FL_TRUNC) != 0;
+        }
+        need_legal = true;
+    } else {                                                             // ---- live step
+        const long long a = load_action(p.actions, p.act_dtype, i);
+        env_step(e, st, p.sd, p.cfg, i, a, r);
+        const bool done = r.terminated || r.truncated;
+        if (p.cfg.validate_mode == SPARC_VALIDATE_EVERY_STEP ||
+            (p.cfg.validate_mode == SPARC_VALIDATE_TERMINAL && done)) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) scratch[k] = e.v[k];
+            scratch[8] = 0;
+            r.rule_flags = validate_env(st, e.puzzle, scratch, e.x, e.y, nullptr) | SPARC_RULE_VALID;
+        }
+#pragma unroll
+        for (int k = 0; k < SPARC_N_STATS; k++) stats[k] = 0;
+        have_stats = true;
+        stats[SPARC_STAT_STEPS] = 1;
+        if (done) {
+            stats[SPARC_STAT_EPISODES] = 1;
+            stats[SPARC_STAT_SOLVED] = r.reward_code == SPARC_R_WIN;
+            stats[SPARC_STAT_FAILED] = r.reward_code == SPARC_R_LOSE;
+            stats[SPARC_STAT_TRUNCATED] = r.truncated;
+            stats[SPARC_STAT_RETURN_CENTS] = (unsigned long long)(long long)e.ep_ret;
+            stats[SPARC_STAT_LENGTH] = e.step;
+            stats[SPARC_STAT_RULES_PASS] = (r.rule_flags & SPARC_RULE_ALL) != 0;
+            if (p.cfg.autoreset == SPARC_AUTORESET_SAME_STEP) {
+                env_reset(e, st, (e.puzzle + (uint32_t)p.cfg.stride) % (uint32_t)st.n_puzzles);
+                need_legal = true;
+            } else {
+                e.flags = FL_DONE | (r.terminated ? FL_TERM : 0) | (r.truncated ? FL_TRUNC : 0);
+            }
+        }
+        store_env(e, p.sd, st, n, i);
+    }
+    if (need_legal) r.legal_mask = env_legal_now(e, st, p.sd, p.cfg, i);
+    // per-env outputs (SG.py:1238)
+    if (p.out.reward_dev) p.out.reward_dev[i] = reward_value(r.reward_code);
+    if (p.out.reward_code_dev) p.out.reward_code_dev[i] = (int8_t)r.reward_code;
+    if (p.out.terminated_dev) p.out.terminated_dev[i] = (uint8_t)r.terminated;
+    if (p.out.truncated_dev) p.out.truncated_dev[i] = (uint8_t)r.truncated;
+    if (p.out.legal_mask_dev) p.out.legal_mask_dev[i] = (uint8_t)r.legal_mask;
+    if (p.out.rule_flags_dev) p.out.rule_flags_dev[i] = (uint16_t)r.rule_flags;
+    if (p.out.step_count_dev) p.out.step_count_dev[i] = (int32_t)e.step;
+    if (p.out.agent_xy_dev) { p.out.agent_xy_dev[2 * i] = (uint8_t)e.x; p.out.agent_xy_dev[2 * i + 1] = (uint8_t)e.y; }
+    return have_stats;
+}

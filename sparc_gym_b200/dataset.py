@@ -31,6 +31,9 @@ from collections import deque
 import numpy as np
 import yaml
 
+_Dumper = getattr(yaml, "CSafeDumper", yaml.SafeDumper)
+_Loader = getattr(yaml, "CSafeLoader", yaml.SafeLoader)
+
 COLOR_NAMES = ["red", "blue", "yellow", "green", "black", "purple", "orange", "white"]
 
 #: rule mixes used by the benchmark configs (BASELINE.json `configs`)
@@ -164,9 +167,12 @@ def shape_id(arr, base=16):
 
 
 def gen_puzzle(w, h, seed, rules=None, *, start=None, end=None, extra_solutions=0,
-               fill=0.6, puzzle_id=None):
+               fill=0.6, puzzle_id=None, text_format="yaml"):
     """One synthetic dataset row. `rules` keys: gaps, dots, stars, squares, triangles,
-    polys, ylops (bools / counts) and colors (1..8)."""
+    polys, ylops (bools / counts) and colors (1..8).  `text_format`: 'yaml' writes
+    `text_visualization` as block-style YAML like the HF dataset; 'json' writes the same
+    document as JSON (a YAML subset the reference's yaml.safe_load reads identically), which
+    both generates and ingests an order of magnitude faster -- used for the big bench pools."""
     rules = dict(rules or {})
     rng = np.random.default_rng([int(seed), w, h, 0x5BA2C])
     X, Y = 2 * w + 1, 2 * h + 1
@@ -281,9 +287,10 @@ def gen_puzzle(w, h, seed, rules=None, *, start=None, end=None, extra_solutions=
         "solution_count": len(sols),
         "solutions": [{"path": [{"x": int(x), "y": int(y)} for x, y in s]} for s in sols],
         "polyshapes": json.dumps(shapes),
-        "text_visualization": yaml.safe_dump(text, sort_keys=False),
+        "text_visualization": (json.dumps(text) if text_format == "json"
+                               else yaml.dump(text, Dumper=_Dumper, sort_keys=False)),
     }
-    row["puzzle_array"] = puzzle_array(row)
+    row["puzzle_array"] = puzzle_array(row, text)
     return row
 
 
@@ -292,13 +299,13 @@ _COL = {"red": "R", "blue": "B", "yellow": "Y", "green": "G", "black": "K", "pur
         "orange": "O", "white": "W"}
 
 
-def puzzle_array(row):
+def puzzle_array(row, text=None):
     """[y][x] symbol grid in the SPaRC text convention (legend: reference
     llm_testing/llm_host.py:102-120): '+' walkable node, 'N' empty rule cell, 'S'/'E' start /
     end, '.' dot, 'G' gap, '<sym>-<colour>' typed cells."""
     X = 2 * row["grid_size"]["width"] + 1
     Y = 2 * row["grid_size"]["height"] + 1
-    tv = yaml.safe_load(row["text_visualization"])["puzzle"]
+    tv = (text or yaml.load(row["text_visualization"], Loader=_Loader))["puzzle"]
     g = [["N" if (x % 2 and y % 2) else "+" for x in range(X)] for y in range(Y)]
     for c in tv["cells"]:
         x, y = c["position"]["x"], c["position"]["y"]
@@ -324,16 +331,17 @@ def gen_pool(n, sizes, rules, seed0=0, **kw):
     return [gen_puzzle(*sizes[i % len(sizes)], seed0 + i, rules, **kw) for i in range(n)]
 
 
-def config_pool(config, n_puzzles=None):
+def config_pool(config, n_puzzles=None, text_format="json"):
     """Puzzle pools of the five BASELINE.json configs."""
+    kw = dict(text_format=text_format)
     if config in (1, "1"):
-        return [gen_puzzle(4, 4, 0, RULES_GAPS_DOTS)]
+        return [gen_puzzle(4, 4, 0, RULES_GAPS_DOTS, **kw)]
     if config in (2, "2"):
-        return gen_pool(n_puzzles or 64, [(4, 4)], RULES_GAPS_DOTS)
+        return gen_pool(n_puzzles or 64, [(4, 4)], RULES_GAPS_DOTS, **kw)
     if config in (3, "3", 5, "5"):
-        return gen_pool(n_puzzles or 1024, [(3, 3), (4, 4), (5, 5), (6, 6)], RULES_FULL, seed0=1000)
+        return gen_pool(n_puzzles or 1024, [(3, 3), (4, 4), (5, 5), (6, 6)], RULES_FULL, seed0=1000, **kw)
     if config in (4, "4"):
-        return gen_pool(n_puzzles or 4096, [(6, 6)], RULES_FULL, seed0=100000)
+        return gen_pool(n_puzzles or 4096, [(6, 6)], RULES_FULL, seed0=100000, **kw)
     raise ValueError(f"unknown config {config!r}")
 
 

@@ -1,0 +1,210 @@
+"""Batched SPaRC environment on one B200: the host-side mirror of the reference's env class
+(SPaRC_Gym/SPaRC_Gym.py:44-1265) for N lockstep instances.
+
+The reference is single-env; this class keeps its vocabulary (`reset`, `step`, observation
+'new' = {'base', 'color', 'additional_info'}, `traceback`, `max_steps`, rewards
+{0, +-0.01, +-1}) and adds the batch dimension in front of every array.  All compute happens in
+libsparc_b200.so (hand-written sm_100a CUDA) through the C ABI in include/sparc_b200.h; torch
+only owns the tensors the kernels write into and the CUDA stream they run on.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import abi
+from .ingest import ingest_rows
+from .store import PuzzleStore
+
+
+class DeviceStore:
+    """A PuzzleStore uploaded to one GPU (SparcStore handle)."""
+
+    def __init__(self, store: PuzzleStore, device):
+        self.host = store
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise abi.SparcError("sparc_gym_b200 runs on CUDA devices only (no CPU fallback)")
+        self.lib = abi.load_library()
+        desc, keep = abi.store_desc(store)
+        handle = C.c_void_p()
+        abi.check(self.lib.sparc_store_create(C.byref(desc), self.device.index or 0, C.byref(handle)))
+        self.handle = handle
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.sparc_store_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _as_store(puzzles, **kw):
+    if isinstance(puzzles, PuzzleStore):
+        return puzzles
+    if puzzles and isinstance(puzzles[0], dict):
+        puzzles = ingest_rows(puzzles)
+    return PuzzleStore(puzzles, **kw)
+
+
+class SparcVecEnv:
+    """N lockstep SPaRC envs on one GPU.
+
+    puzzles        dataset rows / ingested puzzles / a PuzzleStore (shared pool; env i starts on
+                   puzzle i mod pool)
+    traceback, max_steps   as the reference ctor (SG.py:46)
+    autoreset_mode 'next_step' (gymnasium >= 1.0 vector default), 'same_step' or 'disabled'
+    puzzle_stride  on autoreset puzzle p -> (p + stride) mod pool (1 = the reference's cyclic
+                   cursor, SG.py:1087; 0 = same puzzle again)
+    validate       'terminal' | 'every_step' | 'never': when the rule validator
+                   (SG.py:941-950) runs inside step(); its flags land in info['rule_flags']
+    """
+
+    def __init__(self, puzzles, num_envs, traceback=False, max_steps=2000, autoreset_mode="next_step",
+                 puzzle_stride=1, validate="terminal", device="cuda:0", slab=None, planes="auto",
+                 write_obs=True):
+        self.store = _as_store(puzzles, slab=slab, planes=planes) if not isinstance(puzzles, DeviceStore) else puzzles.host
+        self.dstore = puzzles if isinstance(puzzles, DeviceStore) else DeviceStore(self.store, device)
+        self.device = self.dstore.device
+        self.lib = self.dstore.lib
+        self.num_envs = int(num_envs)
+        self.traceback, self.max_steps = bool(traceback), int(max_steps)
+        self.autoreset_mode, self.validate_mode = autoreset_mode, validate
+        handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            abi.check(self.lib.sparc_env_create(self.dstore.handle, self.num_envs, int(self.traceback),
+                                                self.max_steps, abi.AUTORESET[autoreset_mode], int(puzzle_stride),
+                                                abi.VALIDATE[validate], C.byref(handle)))
+        self.handle = handle
+        N, st, dev = self.num_envs, self.store, self.device
+        self.obs = {
+            "base": torch.empty((N, st.n_planes, st.slab_x, st.slab_y), dtype=torch.int32, device=dev),
+            "color": torch.empty((N, st.slab_x, st.slab_y), dtype=torch.int32, device=dev),
+            "additional_info": torch.empty((N, st.slab_x, st.slab_y), dtype=torch.int64, device=dev),
+        }
+        self.reward = torch.zeros(N, dtype=torch.float32, device=dev)
+        self.reward_code = torch.zeros(N, dtype=torch.int8, device=dev)
+        self.terminated = torch.zeros(N, dtype=torch.uint8, device=dev)
+        self.truncated = torch.zeros(N, dtype=torch.uint8, device=dev)
+        self.legal_mask = torch.zeros(N, dtype=torch.uint8, device=dev)
+        self.rule_flags = torch.zeros(N, dtype=torch.int16, device=dev)     # bit pattern of uint16
+        self.step_count = torch.zeros(N, dtype=torch.int32, device=dev)
+        self.agent_xy = torch.zeros((N, 2), dtype=torch.uint8, device=dev)
+        self._stats = torch.zeros(abi.N_STATS, dtype=torch.int64, device=dev)
+        self._obs_out = abi.ObsOut(self.obs["base"].data_ptr(), self.obs["color"].data_ptr(),
+                                   self.obs["additional_info"].data_ptr())
+        self._no_obs = abi.ObsOut(None, None, None)
+        self._step_out = abi.StepOut(self.reward.data_ptr(), self.reward_code.data_ptr(),
+                                     self.terminated.data_ptr(), self.truncated.data_ptr(),
+                                     self.legal_mask.data_ptr(), self.rule_flags.data_ptr(),
+                                     self.step_count.data_ptr(), self.agent_xy.data_ptr())
+        self.write_obs = write_obs
+
+    # -- helpers
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _info(self):
+        return {"legal_mask": self.legal_mask, "rule_flags": self.rule_flags, "reward_code": self.reward_code,
+                "current_step": self.step_count, "agent_location": self.agent_xy}
+
+    # -- reference surface, batched
+    def reset(self, puzzle_idx=None, mask=None):
+        """Clean reset (SG.py:1057-1108 without the plane leak).  `puzzle_idx`:
+        int32[N] puzzle index per env (None = keep each env's current puzzle); `mask`: bool/uint8[N]
+        which envs to reset (None = all)."""
+        idx_ptr = mask_ptr = None
+        if puzzle_idx is not None:
+            self._idx = torch.as_tensor(puzzle_idx, dtype=torch.int32, device=self.device).contiguous()
+            idx_ptr = self._idx.data_ptr()
+        if mask is not None:
+            self._mask = torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
+            mask_ptr = self._mask.data_ptr()
+        with torch.cuda.device(self.device):
+            abi.check(self.lib.sparc_reset(self.handle, idx_ptr, mask_ptr, C.byref(self._step_out),
+                                           C.byref(self._obs_out if self.write_obs else self._no_obs), self._stream()))
+        return self.obs, self._info()
+
+    def step(self, actions):
+        """One lockstep step (SG.py:1111-1238).  `actions`: uint8/int32/int64 CUDA tensor [N]."""
+        if not (isinstance(actions, torch.Tensor) and actions.is_cuda):
+            actions = torch.as_tensor(actions, device=self.device)
+        name = str(actions.dtype).replace("torch.", "")
+        if name not in abi.ACT_DTYPES:
+            actions, name = actions.to(torch.int64), "int64"
+        actions = actions.contiguous()
+        if actions.numel() != self.num_envs:
+            raise ValueError("actions must have one entry per env")
+        with torch.cuda.device(self.device):
+            abi.check(self.lib.sparc_step(self.handle, actions.data_ptr(), abi.ACT_DTYPES[name],
+                                          C.byref(self._step_out),
+                                          C.byref(self._obs_out if self.write_obs else self._no_obs), self._stream()))
+        return self.obs, self.reward, self.terminated, self.truncated, self._info()
+
+    def step_host(self, actions_host, reward_host, terminated_host, truncated_host):
+        """End-to-end step with HOST buffers (numpy / pinned torch CPU tensors): actions are copied
+        to the device, results copied back, stream synchronised (sparc_step_host)."""
+        ptr = lambda a: a.data_ptr() if isinstance(a, torch.Tensor) else a.ctypes.data
+        with torch.cuda.device(self.device):
+            abi.check(self.lib.sparc_step_host(self.handle, ptr(actions_host), ptr(reward_host), ptr(terminated_host),
+                                               ptr(truncated_host),
+                                               C.byref(self._obs_out if self.write_obs else self._no_obs), self._stream()))
+
+    def validate(self, mask=None, region_map=False):
+        """Rule validation of the current state (SG.py:941-950): uint16 flags (as int16 bit
+        patterns) and optionally the region map int8[N, X, Y] (-1 off-cell, SG.py:429-454)."""
+        flags = torch.zeros(self.num_envs, dtype=torch.int16, device=self.device)
+        rmap = torch.empty((self.num_envs, self.store.slab_x, self.store.slab_y), dtype=torch.int8,
+                           device=self.device) if region_map else None
+        mask_ptr = None
+        if mask is not None:
+            self._vmask = torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
+            mask_ptr = self._vmask.data_ptr()
+        with torch.cuda.device(self.device):
+            abi.check(self.lib.sparc_validate(self.handle, mask_ptr, flags.data_ptr(),
+                                              rmap.data_ptr() if region_map else None, self._stream()))
+        return (flags, rmap) if region_map else flags
+
+    def stats(self, clear=False):
+        """Episode statistics since creation / last clear, int64[8] on the device (abi.STAT_NAMES)."""
+        with torch.cuda.device(self.device):
+            abi.check(self.lib.sparc_stats(self.handle, self._stats.data_ptr(), int(clear), self._stream()))
+        return self._stats
+
+    def state_dict(self):
+        n = self.lib.sparc_state_bytes(self.handle)
+        blob = torch.empty(n, dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            abi.check(self.lib.sparc_state_save(self.handle, blob.data_ptr(), self._stream()))
+        return {"state": blob, "num_envs": self.num_envs}
+
+    def load_state_dict(self, sd):
+        blob = sd["state"].to(self.device).contiguous()
+        if blob.numel() != self.lib.sparc_state_bytes(self.handle):
+            raise ValueError("state blob does not match this env")
+        with torch.cuda.device(self.device):
+            abi.check(self.lib.sparc_state_load(self.handle, blob.data_ptr(), self._stream()))
+
+    @property
+    def kernel_launches(self):
+        n = C.c_int64()
+        abi.check(self.lib.sparc_kernel_launches(self.handle, C.byref(n)))
+        return n.value
+
+    def close(self):
+        if getattr(self, "handle", None):
+            torch.cuda.synchronize(self.device)
+            self.lib.sparc_env_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass

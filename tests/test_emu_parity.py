@@ -1,0 +1,62 @@
+"""CPU tests of the product's device code (compiled for the host by tests/emu) against the
+oracle: dynamics, rewards, truncation, traceback, validator, encoder -- everything but the
+GPU execution itself (tests/test_gpu_parity.py does that on the B200)."""
+import numpy as np
+import pytest
+
+from emu.emu_env import EmuVecEnv
+from fuzzrows import fuzz_actions, fuzz_row
+from parity import OracleLockstep, compare
+from sparc_gym_b200.dataset import RULES_FULL, RULES_GAPS_DOTS, gen_pool, gen_puzzle
+
+
+def run_lockstep(make_env, rows, N, T, traceback, max_steps, mode, validate, seed=0, follow=0.5, stride=1):
+    env = make_env(rows, N, traceback=traceback, max_steps=max_steps, autoreset_mode=mode,
+                   validate=validate, puzzle_stride=stride)
+    orc = OracleLockstep(rows, N, env.store.plane_keys, (env.store.slab_x, env.store.slab_y), traceback,
+                         max_steps, autoreset_mode="next_step" if mode == "next_step" else "disabled",
+                         puzzle_stride=stride)
+    exp = orc.reset()
+    out = env.reset()
+    compare((out[0], env.reward, env.terminated, env.truncated, out[1]), exp, "reset")
+    rng = np.random.default_rng(seed)
+    acts = np.stack([np.array(fuzz_actions(rows[i % len(rows)], seed * 1000 + i, T, p_follow=follow)) for i in range(N)], 1)
+    n_done = 0
+    for t in range(T):
+        a = acts[t].astype(np.uint8 if t % 3 == 0 else np.int32 if t % 3 == 1 else np.int64)
+        valid = orc.step(a)
+        exp = orc.expected()
+        res = env.step(a)
+        if validate == "every_step":
+            cf = valid
+        elif validate == "terminal":
+            cf = [v and (exp["terminated"][i] or exp["truncated"][i]) for i, v in enumerate(valid)]
+        else:
+            cf = [False] * N
+        compare(res, exp, f"step {t}", check_flags=cf)
+        n_done += int(sum(orc.done))
+    return env, orc
+
+
+@pytest.mark.parametrize("traceback", [False, True])
+def test_gaps_dots_lockstep(traceback):
+    rows = gen_pool(6, [(4, 4), (3, 3)], RULES_GAPS_DOTS)
+    run_lockstep(EmuVecEnv, rows, 16, 70, traceback, 50, "disabled", "every_step")
+
+
+@pytest.mark.parametrize("traceback", [False, True])
+def test_fuzz_rows_every_step_validation(traceback):
+    rows = [fuzz_row(s) for s in range(200, 236)]
+    run_lockstep(EmuVecEnv, rows, 36, 45, traceback, 40, "disabled", "every_step", seed=3)
+
+
+def test_full_rules_mixed_sizes_terminal_validation():
+    rows = gen_pool(8, [(3, 3), (4, 4), (5, 5), (6, 6)], RULES_FULL, seed0=40, extra_solutions=1)
+    run_lockstep(EmuVecEnv, rows, 24, 90, True, 80, "disabled", "terminal", seed=5, follow=0.97)
+
+
+def test_autoreset_next_step_cycles_puzzles():
+    rows = gen_pool(5, [(2, 2), (3, 3)], RULES_FULL, seed0=7)
+    env, orc = run_lockstep(EmuVecEnv, rows, 10, 120, False, 25, "next_step", "terminal", seed=9, follow=0.3)
+    st = env.stats()
+    assert st[0] > 10 and st[4] > 0          # episodes finished, steps counted
