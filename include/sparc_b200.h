@@ -80,7 +80,8 @@ typedef struct {                 /* 32 bytes */
     uint8_t  start_x, start_y;   /* SG.py:267 */
     uint8_t  target_x, target_y; /* SG.py:268 */
     uint8_t  n_shapes;           /* shape slots of this puzzle */
-    uint8_t  flags;              /* bit0: solution_count > 0 */
+    uint8_t  flags;              /* bit0: solution_count > 0; bit1: has stars / squares / shape instances
+                                    (a region rule can fail, so the validator must segment regions) */
     uint32_t shape_off;          /* index of the first SparcShape */
     uint32_t trie_root;          /* trie node of the start location, 0 = no listed solution starts there */
     int32_t  solution_count;
@@ -134,7 +135,9 @@ typedef struct {                 /* all pointers are HOST pointers; copied by sp
     const uint64_t* cell_boards;        /* [n_puzzles][SPARC_N_CELL_BOARDS] */
     const uint32_t* static_bits;        /* [n_puzzles][words_per_puzzle]: the observation's one-hot
                                            planes in output order, bit-packed, dynamic planes zero */
-    const uint8_t*  color;              /* [n_puzzles][slab_x*slab_y]  (SG.py:279, 309-315) */
+    const uint32_t* color4;             /* [n_puzzles][ceil(4*slab_x*slab_y/32)]: colour ids 0..8, 4 bits per
+                                           node, dense slab order  (SG.py:279, 309-315) */
+    const uint32_t* info_nz;            /* [n_puzzles][ceil(slab_x*slab_y/32)]: additional_info != 0 */
     const int32_t*  info;               /* [n_puzzles][slab_x*slab_y]  (SG.py:280, 318-325) */
     const SparcShape* shapes;           /* [n_shapes_total] */
     const uint32_t* trie;               /* [n_trie_nodes][8] */

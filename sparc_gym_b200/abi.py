@@ -13,7 +13,8 @@ import subprocess
 import numpy as np
 
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
-LIB_PATH = os.path.join(CSRC, "libsparc_b200.so")
+# SPARC_B200_LIB selects another build of the same CUDA library (kernel tuning experiments)
+LIB_PATH = os.environ.get("SPARC_B200_LIB") or os.path.join(CSRC, "libsparc_b200.so")
 REPO_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -44,7 +45,7 @@ class StoreDesc(C.Structure):
                 ("words_per_puzzle", C.c_int32), ("n_shapes_total", C.c_int32),
                 ("n_trie_nodes", C.c_int32),
                 ("headers", C.c_void_p), ("node_boards", C.c_void_p), ("cell_boards", C.c_void_p),
-                ("static_bits", C.c_void_p), ("color", C.c_void_p), ("info", C.c_void_p),
+                ("static_bits", C.c_void_p), ("color4", C.c_void_p), ("info_nz", C.c_void_p), ("info", C.c_void_p),
                 ("shapes", C.c_void_p), ("trie", C.c_void_p)]
 
 
@@ -132,7 +133,7 @@ def store_desc(store):
     keep = []
     for field, arr in (("headers", store.headers), ("node_boards", store.node_boards),
                        ("cell_boards", store.cell_boards), ("static_bits", store.static_bits),
-                       ("color", store.color), ("info", store.info), ("shapes", store.shapes),
+                       ("color4", store.color4), ("info_nz", store.info_nz), ("info", store.info), ("shapes", store.shapes),
                        ("trie", store.trie)):
         a = np.ascontiguousarray(arr)
         keep.append(a)

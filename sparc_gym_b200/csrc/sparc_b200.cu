@@ -14,6 +14,9 @@
 #include "sparc_core.cuh"
 
 #define CTA_THREADS 128
+#ifndef SPARC_MINBLOCKS          // resident CTAs per SM the register allocator must allow.  8 -> 64
+#define SPARC_MINBLOCKS 8        // registers: the rarely-run validator spills, the streaming encoder
+#endif                           // gets 2x the resident warps (measured: 0.322 -> 0.219 ms/step, config 4)
 
 static thread_local char g_err[512] = "";
 static int fail(int code, const char* fmt, const char* detail = "") {
@@ -29,7 +32,7 @@ static int fail(int code, const char* fmt, const char* detail = "") {
 struct SparcStore {
     int device;
     StoreDev d;
-    void* blocks[8];
+    void* blocks[9];
     int plane_ids[SPARC_MAX_PLANES];
 };
 
@@ -45,24 +48,25 @@ struct SparcEnv {
     uint8_t* trunc_stage;
 };
 
-// dynamic shared: rows[tile][Wpad] | tile_puzzle[tile]
+// dynamic shared (tile_smem_words): dyn[tile][9] | tile_puzzle[tile] | flat | cflat | zflat
 extern __shared__ uint32_t smem[];
 
-__global__ void __launch_bounds__(CTA_THREADS) k_env(const KParams p) {
+__global__ void __launch_bounds__(CTA_THREADS, SPARC_MINBLOCKS) k_env(const KParams p) {
     const StoreDev& st = p.st;
     const int tid = threadIdx.x;
     const long long env0 = (long long)blockIdx.x * p.tile;
     const long long n = p.cfg.n_envs;
     const int nE = (int)min((long long)p.tile, n - env0);
-    uint32_t* rows = smem;
-    uint32_t* tile_puzzle = smem + (size_t)p.tile * st.Wpad;
+    uint32_t* dyn = smem;
+    uint32_t* tile_puzzle = smem + p.tile * SPARC_DYN_STRIDE;
 
     EnvRegs e;
     unsigned long long my_stats[SPARC_N_STATS];
     bool have_stats = false;
     if (tid < nE) {
-        have_stats = phase_a(p, env0 + tid, e, rows + tid * st.Wpad, my_stats);
+        have_stats = phase_a(p, env0 + tid, e, dyn + tid * SPARC_DYN_STRIDE, my_stats);
         tile_puzzle[tid] = e.puzzle;
+        write_dyn(st, dyn, tid, e);
     }
     // statistics: warp-reduce, one atomic per counter per warp (the dynamics threads are the first warps)
     if (p.mode == 0 && tid < ((nE + 31) & ~31)) {
@@ -76,15 +80,9 @@ __global__ void __launch_bounds__(CTA_THREADS) k_env(const KParams p) {
     }
     if (!p.obs.base_dev && !p.obs.color_dev && !p.obs.info_dev) return;
     __syncthreads();
-    if (p.obs.base_dev) {
-        stage_static(st, rows, tile_puzzle, nE, tid, CTA_THREADS);
-        __syncthreads();
-        if (tid < nE) stage_dynamic(st, rows, tid, e);
-        __syncthreads();
-        expand_base(st, rows, p.obs.base_dev + (size_t)env0 * st.L, nE, tid, CTA_THREADS);
-    }
-    if (p.obs.color_dev) expand_color(st, tile_puzzle, p.obs.color_dev + (size_t)env0 * st.S, nE, tid, CTA_THREADS);
-    if (p.obs.info_dev) expand_info(st, tile_puzzle, p.obs.info_dev + (size_t)env0 * st.S, nE, tid, CTA_THREADS);
+    encode_tile_stage1(st, smem, p.tile, nE, p.obs, tid, CTA_THREADS);
+    __syncthreads();
+    encode_tile_stage2(st, smem, p.tile, nE, env0, p.obs, tid, CTA_THREADS);
 }
 
 // stand-alone validator (SG.py:941-950) for sparc_validate: one env per thread
@@ -152,14 +150,17 @@ int sparc_store_create(const SparcStoreDesc* desc, int device, SparcStore** out)
     d.n_puzzles = desc->n_puzzles; d.SX = desc->slab_x; d.SY = desc->slab_y; d.S = d.SX * d.SY;
     d.P = desc->n_planes; d.L = d.P * d.S; d.W = (d.L + 31) / 32;
     if (desc->words_per_puzzle != d.W) { delete s; return fail(SPARC_E_ARG, "words_per_puzzle mismatch%s"); }
-    d.Wpad = (d.W + 1 > 9 ? d.W + 1 : 9) | 1;       // odd stride (bank-conflict free), >= 9 words of scratch
     d.nv = (d.S + 31) / 32;
+    d.inv_L = (uint32_t)((1ull << 32) / (uint64_t)d.L) + 1u;
+    d.inv_S = (uint32_t)((1ull << 32) / (uint64_t)d.S) + 1u;
+    d.inv_4S = (uint32_t)((1ull << 32) / (uint64_t)(4 * d.S)) + 1u;
+    d.Wc = (4 * d.S + 31) / 32;
     memcpy(s->plane_ids, desc->plane_ids, sizeof(s->plane_ids));
     const size_t n = desc->n_puzzles;
     int rc;
     if ((rc = upload(desc->headers, n, &d.hdr, &s->blocks[0])) || (rc = upload(desc->node_boards, n * SPARC_N_NODE_BOARDS * 8, &d.nb, &s->blocks[1])) ||
         (rc = upload(desc->cell_boards, n * SPARC_N_CELL_BOARDS, &d.cb, &s->blocks[2])) || (rc = upload(desc->static_bits, n * d.W, &d.sbits, &s->blocks[3])) ||
-        (rc = upload(desc->color, n * d.S, &d.color, &s->blocks[4])) || (rc = upload(desc->info, n * d.S, &d.info, &s->blocks[5])) ||
+        (rc = upload(desc->color4, n * d.Wc, &d.color4, &s->blocks[4])) || (rc = upload(desc->info_nz, n * d.nv, &d.info_nz, &s->blocks[8])) || (rc = upload(desc->info, n * d.S, &d.info, &s->blocks[5])) ||
         (rc = upload(desc->shapes, (size_t)desc->n_shapes_total, &d.shapes, &s->blocks[6])) ||
         (rc = upload(desc->trie, (size_t)desc->n_trie_nodes * SPARC_TRIE_NODE_WORDS, &d.trie, &s->blocks[7]))) {
         sparc_store_destroy(s);
@@ -231,7 +232,7 @@ static int launch_env(SparcEnv* e, KParams& p, void* stream) {
     p.st = e->store->d; p.sd = e->s; p.cfg = e->cfg; p.tile = e->tile;
     const int64_t n = e->cfg.n_envs;
     const unsigned grid = (unsigned)((n + e->tile - 1) / e->tile);
-    const size_t shmem = ((size_t)e->tile * p.st.Wpad + e->tile) * sizeof(uint32_t);
+    const size_t shmem = (size_t)tile_smem_words(p.st, e->tile) * sizeof(uint32_t);
     k_env<<<grid, CTA_THREADS, shmem, (cudaStream_t)stream>>>(p);
     CU(cudaGetLastError());
     e->launches++;

@@ -10,6 +10,15 @@
 #include <stdint.h>
 #include "../../include/sparc_b200.h"
 
+#if defined(SPARC_EMU_COUNTERS)
+static long long g_fit_iters = 0, g_fit_calls = 0, g_fit_max = 0, g_fit_cur = 0;   // search effort of exact_fit (tests only)
+#define SPARC_COUNT_FIT() (++g_fit_iters, ++g_fit_cur, g_fit_max = g_fit_cur > g_fit_max ? g_fit_cur : g_fit_max)
+#define SPARC_COUNT_FIT_CALL() (++g_fit_calls, g_fit_cur = 0)
+#else
+#define SPARC_COUNT_FIT() ((void)0)
+#define SPARC_COUNT_FIT_CALL() ((void)0)
+#endif
+
 #if defined(__CUDACC__)
 #define SPARC_HD __host__ __device__ __forceinline__
 #define SPARC_D __device__ __forceinline__
@@ -31,9 +40,14 @@ SPARC_D uint32_t sp_funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) { return __f
 template <typename T> SPARC_D T sp_ldg(const T* p) { return __ldg(p); }
 struct sp_u4 { uint32_t x, y, z, w; };
 SPARC_D sp_u4 sp_ldg4(const uint32_t* p) { uint4 v = __ldg(reinterpret_cast<const uint4*>(p)); return {v.x, v.y, v.z, v.w}; }
-// streaming 128-bit store: the observation is written once and not re-read by this kernel
+SPARC_D uint32_t sp_umulhi(uint32_t a, uint32_t b) { return __umulhi(a, b); }
+// streaming 128-bit store (st.global.cs): the observation is written once and not re-read by this kernel
 SPARC_D void sp_st4(int32_t* p, int32_t a, int32_t b, int32_t c, int32_t d) {
-    asm volatile("st.global.cs.v4.s32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+#if defined(SPARC_STORE_PLAIN)
+    *reinterpret_cast<int4*>(p) = make_int4(a, b, c, d);
+#else
+    __stcs(reinterpret_cast<int4*>(p), make_int4(a, b, c, d));
+#endif
 }
 #else
 SPARC_HD uint32_t sp_brev(uint32_t v) {
@@ -50,6 +64,7 @@ SPARC_HD int sp_ffsll(uint64_t v) { return __builtin_ffsll((long long)v); }
 SPARC_HD uint32_t sp_funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) {
     sh &= 31; return sh ? (lo >> sh) | (hi << (32 - sh)) : lo;
 }
+SPARC_HD uint32_t sp_umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
 template <typename T> SPARC_HD T sp_ldg(const T* p) { return *p; }
 struct sp_u4 { uint32_t x, y, z, w; };
 SPARC_HD sp_u4 sp_ldg4(const uint32_t* p) { return {p[0], p[1], p[2], p[3]}; }
@@ -61,13 +76,16 @@ SPARC_HD void sp_st4(int32_t* p, int32_t a, int32_t b, int32_t c, int32_t d) { p
 // ---------------------------------------------------------------------------------------------
 struct StoreDev {
     int n_puzzles, SX, SY, S;      // slab lattice, S = SX*SY nodes
-    int P, L, W, Wpad;             // planes, L = P*S bits per env, W words, padded (odd, >= 9) row stride
+    int P, L, W;                   // planes, L = P*S bits per env, W = ceil(L/32) words
     int nv;                        // words of one dense plane: ceil(S/32)
+    int Wc;                        // words of the 4-bit colour string: ceil(4S/32)
+    uint32_t inv_L, inv_S, inv_4S; // floor(2^32/d)+1: exact x/d by one mul-hi for the x used here
     const SparcPuzzleHeader* hdr;
     const uint32_t* nb;            // [n][SPARC_N_NODE_BOARDS][8]
     const uint64_t* cb;            // [n][SPARC_N_CELL_BOARDS]
     const uint32_t* sbits;         // [n][W]
-    const uint8_t* color;          // [n][S]
+    const uint32_t* color4;        // [n][Wc]  colour ids, 4 bits per node, dense slab order
+    const uint32_t* info_nz;       // [n][nv]  additional_info != 0
     const int32_t* info;           // [n][S]
     const SparcShape* shapes;
     const uint32_t* trie;          // [nodes][8]
@@ -301,11 +319,14 @@ SPARC_HD uint64_t shape_place(const SparcShape& s, int cx, int cy, int w, int h)
     return s.mask << (cx * 8 + y0);
 }
 
-// exact-fit existence (SG.py:738-895): ylops first (any rule-cell anchor, may leave the region,
-// may stack), then polys anchored at the first still-demanded cell.  n_poly / n_ylop: instances
-// per shape slot inside this region.
-SPARC_HD bool exact_fit(uint64_t region, int w, int h, const SparcShape* shapes, int ns,
+// exact-fit existence in the REFERENCE's search order (SG.py:738-895): all ylops first (any
+// rule-cell anchor, may leave the region, may stack), then polys anchored at the first
+// still-demanded cell.  Exponential in the number of ylops (49^k anchor combinations), so the
+// kernels use exact_fit() below; this version is kept as an independent cross-check for the
+// tests (tests/emu).  n_poly / n_ylop: instances per shape slot inside this region.
+SPARC_HD bool exact_fit_reference_order(uint64_t region, int w, int h, const SparcShape* shapes, int ns,
                         const uint8_t* n_poly, const uint8_t* n_ylop) {
+    SPARC_COUNT_FIT_CALL();
     uint8_t rem[SPARC_MAX_SHAPES];
     uint8_t ylist[SPARC_MAX_YLOPS];
     uint8_t fr_item[64], fr_pos[64];
@@ -318,6 +339,7 @@ SPARC_HD bool exact_fit(uint64_t region, int w, int h, const SparcShape* shapes,
     Cnt3 c = {region, 0, 0};
     int level = 0, it = 0;
     for (;;) {
+        SPARC_COUNT_FIT();
         bool found = false;
         if (level < ny) {                                   // SG.py:794-816
             const SparcShape& sh = shapes[ylist[level]];
@@ -351,6 +373,105 @@ SPARC_HD bool exact_fit(uint64_t region, int w, int h, const SparcShape* shapes,
             const int s = fr_item[level], t = fr_pos[level];
             cnt_add(c, shape_place(shapes[s], t >> 3, t & 7, w, h)); rem[s]++;
             it = s + 1;
+        }
+    }
+}
+
+// signed 4-bit bit-sliced per-cell counters (two's complement, -8..7): net demand of a cell =
+// [cell in region] + ylops covering it - polys covering it
+struct Cnt4 { uint64_t b0, b1, b2, b3; };
+SPARC_HD void cnt4_add(Cnt4& c, uint64_t m) {
+    uint64_t t = c.b0 & m; c.b0 ^= m; m = t; t = c.b1 & m; c.b1 ^= m; m = t; t = c.b2 & m; c.b2 ^= m; c.b3 ^= t;
+}
+SPARC_HD void cnt4_sub(Cnt4& c, uint64_t m) {
+    uint64_t t = ~c.b0 & m; c.b0 ^= m; m = t; t = ~c.b1 & m; c.b1 ^= m; m = t; t = ~c.b2 & m; c.b2 ^= m; c.b3 ^= t;
+}
+SPARC_HD int cnt4_get(const Cnt4& c, int bit) {
+    return (int)((c.b0 >> bit) & 1) + 2 * (int)((c.b1 >> bit) & 1) + 4 * (int)((c.b2 >> bit) & 1) - 8 * (int)((c.b3 >> bit) & 1);
+}
+// cells whose value equals the small constant k (-8..7)
+SPARC_HD uint64_t cnt4_eq(const Cnt4& c, int k) {
+    const uint64_t z = 0, o = ~z;
+    return ~(c.b0 ^ ((k & 1) ? o : z)) & ~(c.b1 ^ ((k & 2) ? o : z)) & ~(c.b2 ^ ((k & 4) ? o : z)) & ~(c.b3 ^ ((k & 8) ? o : z));
+}
+
+// exact-fit existence (SG.py:738-895).  The reference accepts iff there is a placement of every
+// ylop (anchor on any rule cell, all cells inside the grid, may leave the region, may stack) and
+// of every non-empty poly (translation only) such that on every cell
+//        #polys covering - #ylops covering == [cell in region].
+// (Its own search places all ylops first -- 49^k anchor combinations -- and then anchors polys
+// at the first still-demanded cell; SG.py:794-853.)  The same existence question is answered
+// here by ONE sweep over the cells in (x, y) order: every shape is anchored at its
+// lexicographically first cell (SG.py:864-865), so when the sweep reaches cell c everything
+// that can still touch c must be anchored AT c; we choose the ylops and polys anchored at c
+// (canonical non-decreasing slot order) so that c ends at exactly zero, then move on.  A ylop
+// is therefore only ever tried where polys can absorb it, and a dead cell is detected once,
+// not once per ylop combination.
+SPARC_HD bool exact_fit(uint64_t region, int w, int h, const SparcShape* shapes, int ns,
+                        const uint8_t* n_poly, const uint8_t* n_ylop) {
+    SPARC_COUNT_FIT_CALL();
+    uint8_t rem_p[SPARC_MAX_SHAPES], rem_y[SPARC_MAX_SHAPES];
+    uint8_t fr_cell[128], fr_q[128];                          // DFS edges: q < 2ns placement, 0xFF = advance
+    int tot_p = 0, tot_y = 0;
+    for (int s = 0; s < ns; s++) {
+        const int empty = (shapes[s].flags & 2) != 0;         // zero-area shapes never touch the grid
+        rem_p[s] = empty ? 0 : n_poly[s];
+        rem_y[s] = empty ? 0 : n_ylop[s];
+        if ((shapes[s].flags & 1) && (rem_p[s] | rem_y[s])) return false;   // can never be placed
+        tot_p += rem_p[s]; tot_y += rem_y[s];
+    }
+    if (tot_y > SPARC_MAX_YLOPS) return false;                // (ingest guarantees this never happens)
+    Cnt4 c = {region, 0, 0, 0};
+    uint64_t grid = 0;
+    for (int cx = 0; cx < w; cx++) grid |= ((1ull << h) - 1ull) << (cx * 8);
+    int level = 0, cell = 0, q = 0;
+    for (;;) {
+        SPARC_COUNT_FIT();
+        const int n = cnt4_get(c, cell);
+        const uint64_t later = grid & ~((2ull << cell) - 1ull);               // cells after `cell`
+        bool found = false;
+        for (int qq = q; qq < 2 * ns; qq++) {
+            if (qq < ns) {                                                    // anchor a ylop here
+                if (!rem_y[qq] || n + 1 > tot_p) continue;
+                const uint64_t m = shape_place(shapes[qq], cell >> 3, cell & 7, w, h);
+                if (!m) continue;
+                // one ylop fewer can lift later cells: those already at the floor would be lost
+                if (cnt4_eq(c, -tot_y) & later & ~m) continue;
+                cnt4_add(c, m); rem_y[qq]--; tot_y--;
+            } else {                                                          // anchor a poly here
+                const int s = qq - ns;
+                if (n <= 0) break;                                            // nothing left to cover at this cell
+                if (!rem_p[s]) continue;
+                const uint64_t m = shape_place(shapes[s], cell >> 3, cell & 7, w, h);
+                if (!m) continue;
+                if (cnt4_eq(c, -tot_y) & later & m) continue;                 // would sink below what ylops can lift
+                cnt4_sub(c, m); rem_p[s]--; tot_p--;
+            }
+            fr_cell[level] = (uint8_t)cell; fr_q[level] = (uint8_t)qq; level++;
+            q = qq; found = true;
+            break;
+        }
+        if (found) continue;
+        if (cnt4_get(c, cell) == 0) {                                         // settled: advance
+            if (!later) { if (tot_p == 0 && tot_y == 0) return true; }
+            else if (tot_p + tot_y == 0) {
+                if (((c.b0 | c.b1 | c.b2 | c.b3) & later) == 0) return true;  // nothing left and nothing demanded
+            } else {
+                fr_cell[level] = (uint8_t)cell; fr_q[level] = 0xFF; level++;
+                cell = sp_ffsll(later) - 1; q = 0;
+                continue;
+            }
+        }
+        for (;;) {                                                            // backtrack
+            if (level == 0) return false;
+            level--;
+            cell = fr_cell[level];
+            const int qq = fr_q[level];
+            if (qq == 0xFF) continue;                                         // advance was the last child
+            if (qq < ns) { cnt4_sub(c, shape_place(shapes[qq], cell >> 3, cell & 7, w, h)); rem_y[qq]++; tot_y++; }
+            else { cnt4_add(c, shape_place(shapes[qq - ns], cell >> 3, cell & 7, w, h)); rem_p[qq - ns]++; tot_p++; }
+            q = qq + 1;
+            break;
         }
     }
 }
@@ -407,7 +528,14 @@ SPARC_HD int validate_env(const StoreDev& st, uint32_t puzzle, const uint32_t* v
         }
         if (!bad) flags |= SPARC_RULE_TRIANGLES;
     }
-    // regions (SG.py:422-454): passable = rule cell, or neither gap nor path (Q6)
+    // regions (SG.py:422-454): passable = rule cell, or neither gap nor path (Q6).  The three
+    // region rules are vacuously true for a puzzle without stars, squares and shape instances,
+    // so its region pass is skipped unless the caller wants the region map itself.
+    if (!(h.flags & 2) && !region_map) {
+        flags |= SPARC_RULE_SQUARES | SPARC_RULE_STARS | SPARC_RULE_POLY_YLOP;
+        if ((flags & 0xFF) == 0xFF) flags |= SPARC_RULE_ALL;
+        return flags;
+    }
     uint32_t Pm[8], unl[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) { Pm[k] = VAL[k] & (C[k] | ~(G[k] | V[k])); unl[k] = C[k]; }
@@ -503,99 +631,147 @@ SPARC_HD int validate_env(const StoreDev& st, uint32_t puzzle, const uint32_t* v
 
 // ---------------------------------------------------------------------------------------------
 // observation encoder (SG.py:956-979 with a full rewrite in the reference dtypes)
-//   rows : shared staging, one row of Wpad words per env of the tile = the env's P one-hot
-//          planes bit-packed in output order
 //   tile : nE consecutive envs starting at env0 (env0 % 4 == 0 keeps every stream 16-B aligned)
+//   dyn  : shared, SPARC_DYN_STRIDE words per env: visited plane (dense, 8 words) + bit index of
+//          the agent inside the env's L-bit plane string
+//   flat : shared, the tile's one-hot planes as ONE bit string in output element order
+//          (env j occupies bits [j*L, (j+1)*L)), so that output chunk c (4 consecutive int32 of
+//          the tile's contiguous [nE][P][SX][SY] block) is simply nibble c of the string
 // ---------------------------------------------------------------------------------------------
-// stage 1 (cooperative): static planes of each env's puzzle -> rows
-SPARC_HD void stage_static(const StoreDev& st, uint32_t* rows, const uint32_t* tile_puzzle, int nE, int tid, int nthr) {
-    const int total = nE * st.W;
-    for (int idx = tid; idx < total; idx += nthr) {
-        const int j = idx / st.W, k = idx - j * st.W;
-        rows[j * st.Wpad + k] = sp_ldg(st.sbits + (size_t)tile_puzzle[j] * st.W + k);
+#define SPARC_DYN_STRIDE 9
+
+SPARC_HD void write_dyn(const StoreDev& st, uint32_t* dyn, int j, const EnvRegs& e) {
+    uint32_t* row = dyn + j * SPARC_DYN_STRIDE;
+#pragma unroll
+    for (int k = 0; k < 8; k++) row[k] = e.v[k];
+    row[8] = (uint32_t)(2 * st.S + e.x * st.SY + e.y);       // agent_location is plane 2
+}
+
+// bit-string sources: word k of env j's string
+struct PlaneSrc {                       // the P one-hot planes: static planes of the puzzle | visited (plane 0) | agent bit
+    const StoreDev& st; const uint32_t* dyn; const uint32_t* tile_puzzle;
+    SPARC_HD uint32_t word(int j, int k) const {
+        const uint32_t* row = dyn + j * SPARC_DYN_STRIDE;
+        uint32_t w = sp_ldg(st.sbits + (size_t)tile_puzzle[j] * st.W + k);
+        if (k < st.nv) w |= row[k];
+        const uint32_t ab = row[8];
+        if ((int)(ab >> 5) == k) w |= 1u << (ab & 31);
+        return w;
+    }
+};
+struct ColorSrc {                       // colour plane, 4 bits per node
+    const StoreDev& st; const uint32_t* tile_puzzle;
+    SPARC_HD uint32_t word(int j, int k) const { return sp_ldg(st.color4 + (size_t)tile_puzzle[j] * st.Wc + k); }
+};
+struct InfoNzSrc {                      // additional_info != 0, 1 bit per node
+    const StoreDev& st; const uint32_t* tile_puzzle;
+    SPARC_HD uint32_t word(int j, int k) const { return sp_ldg(st.info_nz + (size_t)tile_puzzle[j] * st.nv + k); }
+};
+
+// stage 1 (cooperative): concatenate the envs' L-bit strings (W words each at the source) into
+// one flat bit string: env j occupies bits [j*L, (j+1)*L).
+template <class Src>
+SPARC_HD void build_flat(const Src& src, uint32_t* flat, int nE, int L, int W, uint32_t inv_L, int tid, int nthr) {
+    const int nwords = (nE * L + 31) >> 5;
+    for (int f = tid; f < nwords; f += nthr) {
+        const uint32_t b = 32u * (uint32_t)f;
+        int j = (int)sp_umulhi(b, inv_L);
+        int r = (int)b - j * L;
+        uint32_t v = 0;
+        int filled = 0;
+        do {                                                    // usually 1 pass, 2 at an env boundary
+            const int k = r >> 5, sh = r & 31;
+            const uint32_t lo = src.word(j, k);
+            const uint32_t hi = (sh && k + 1 < W) ? src.word(j, k + 1) : 0u;
+            uint32_t bits = sp_funnel_r(lo, hi, sh);
+            const int nb = L - r;                               // bits env j still owns from r on
+            if (nb < 32) bits &= (1u << nb) - 1u;
+            v |= bits << filled;
+            filled += nb;
+            j++; r = 0;
+        } while (filled < 32 && j < nE);
+        flat[f] = v;
     }
 }
-// stage 2 (owner thread of env j): OR in the dynamic planes: visited = plane 0, agent = plane 2
-SPARC_HD void stage_dynamic(const StoreDev& st, uint32_t* rows, int j, const EnvRegs& e) {
-    uint32_t* row = rows + j * st.Wpad;
-#pragma unroll
-    for (int k = 0; k < 8; k++) if (k < st.nv) row[k] |= e.v[k];
-    const int ab = 2 * st.S + e.x * st.SY + e.y;
-    row[ab >> 5] |= 1u << (ab & 31);
-}
-// stage 3 (cooperative): expand bits to int32, 16 bytes per store, consecutive threads ->
-// consecutive 16-byte chunks of the tile's contiguous [nE][P][SX][SY] block
-SPARC_HD void expand_base(const StoreDev& st, const uint32_t* rows, int32_t* out_tile, int nE, int tid, int nthr) {
-    const int L = st.L;
-    const int total = nE * L;
+// stage 2 (cooperative): expand bits to int32, 16 bytes per store, consecutive threads ->
+// consecutive 16-byte chunks (coalesced 512-byte warp stores)
+SPARC_HD void expand_flat(const uint32_t* flat, int32_t* out_tile, int total, int tid, int nthr) {
     const int nchunks = total >> 2;
-    int e0 = tid * 4;
-    int j = e0 / L, r0 = e0 - j * L;
-    const int adv = nthr * 4;
+    int c = tid;
+    for (; c + 3 * nthr < nchunks; c += 4 * nthr) {             // 4 independent stores in flight per thread
+        uint32_t n[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) { const int cc = c + u * nthr; n[u] = flat[cc >> 3] >> ((cc & 7) * 4); }
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            sp_st4(out_tile + 4 * (size_t)(c + u * nthr), n[u] & 1, (n[u] >> 1) & 1, (n[u] >> 2) & 1, (n[u] >> 3) & 1);
+    }
+    for (; c < nchunks; c += nthr) {
+        const uint32_t n = flat[c >> 3] >> ((c & 7) * 4);
+        sp_st4(out_tile + 4 * (size_t)c, n & 1, (n >> 1) & 1, (n >> 2) & 1, (n >> 3) & 1);
+    }
+    for (int e = (nchunks << 2) + tid; e < total; e += nthr)    // tail (< 4 elements)
+        out_tile[e] = (flat[e >> 5] >> (e & 31)) & 1u;
+}
+// colour plane: flat string of 4-bit colour ids -> int32 output (chunk c = 16 bits at 16c)
+SPARC_HD void expand_color(const uint32_t* cflat, int32_t* out_tile, int total, int tid, int nthr) {
+    const int nchunks = total >> 2;
     for (int c = tid; c < nchunks; c += nthr) {
-        uint32_t nib;
-        if (r0 + 3 < L) {
-            const uint32_t* rp = rows + j * st.Wpad + (r0 >> 5);
-            nib = sp_funnel_r(rp[0], rp[1], r0 & 31);
-        } else {                                            // chunk straddles two envs
-            nib = 0;
-            for (int q = 0; q < 4; q++) {
-                int rr = r0 + q, jj = j;
-                if (rr >= L) { rr -= L; jj++; }
-                nib |= ((rows[jj * st.Wpad + (rr >> 5)] >> (rr & 31)) & 1u) << q;
+        const uint32_t n = cflat[c >> 1] >> ((c & 1) * 16);
+        sp_st4(out_tile + 4 * (size_t)c, n & 15, (n >> 4) & 15, (n >> 8) & 15, (n >> 12) & 15);
+    }
+    for (int e = (nchunks << 2) + tid; e < total; e += nthr)
+        out_tile[e] = (cflat[e >> 3] >> ((e & 7) * 4)) & 15u;
+}
+// additional_info plane -> int64 output (two elements per 16-byte store).  The plane is almost
+// all zeros: the flat non-zero mask decides, and only marked nodes read their int32 value.
+SPARC_HD void expand_info(const StoreDev& st, const uint32_t* zflat, const uint32_t* tile_puzzle, int64_t* out_tile,
+                          int nE, int tid, int nthr) {
+    const int S = st.S, total = nE * S, nchunks = total >> 1;
+    for (int c = tid; c < nchunks; c += nthr) {
+        const uint32_t m = (zflat[c >> 4] >> ((c & 15) * 2)) & 3u;
+        int32_t a = 0, b = 0;
+        if (m) {
+            const uint32_t e0 = 2u * (uint32_t)c;
+            const int j = (int)sp_umulhi(e0, st.inv_S), r = (int)e0 - j * S;
+            if (m & 1) a = sp_ldg(st.info + (size_t)tile_puzzle[j] * S + r);
+            if (m & 2) {
+                const int j2 = (r + 1 >= S) ? j + 1 : j, r2 = (r + 1 >= S) ? 0 : r + 1;
+                b = sp_ldg(st.info + (size_t)tile_puzzle[j2] * S + r2);
             }
         }
-        sp_st4(out_tile + 4 * (size_t)c, nib & 1, (nib >> 1) & 1, (nib >> 2) & 1, (nib >> 3) & 1);
-        r0 += adv;
-        while (r0 >= L) { r0 -= L; j++; }
-    }
-    for (int e = (nchunks << 2) + tid; e < total; e += nthr) {       // tail (< 4 elements)
-        const int jj = e / L, rr = e - jj * L;
-        out_tile[e] = (rows[jj * st.Wpad + (rr >> 5)] >> (rr & 31)) & 1u;
-    }
-}
-// colour plane: uint8 store -> int32 output
-SPARC_HD void expand_color(const StoreDev& st, const uint32_t* tile_puzzle, int32_t* out_tile, int nE, int tid, int nthr) {
-    const int S = st.S, total = nE * S, nchunks = total >> 2;
-    int e0 = tid * 4;
-    int j = e0 / S, r0 = e0 - j * S;
-    const int adv = nthr * 4;
-    for (int c = tid; c < nchunks; c += nthr) {
-        int32_t v[4];
-        int jj = j, rr = r0;
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            v[q] = sp_ldg(st.color + (size_t)tile_puzzle[jj] * S + rr);
-            if (++rr >= S) { rr = 0; jj++; if (jj >= nE) jj = nE - 1; }
-        }
-        sp_st4(out_tile + 4 * (size_t)c, v[0], v[1], v[2], v[3]);
-        r0 += adv;
-        while (r0 >= S) { r0 -= S; j++; }
-    }
-    for (int e = (nchunks << 2) + tid; e < total; e += nthr) {
-        const int jj = e / S, rr = e - jj * S;
-        out_tile[e] = sp_ldg(st.color + (size_t)tile_puzzle[jj] * S + rr);
-    }
-}
-// additional_info plane: int32 store -> int64 output (two elements per 16-byte store)
-SPARC_HD void expand_info(const StoreDev& st, const uint32_t* tile_puzzle, int64_t* out_tile, int nE, int tid, int nthr) {
-    const int S = st.S, total = nE * S, nchunks = total >> 1;
-    int e0 = tid * 2;
-    int j = e0 / S, r0 = e0 - j * S;
-    const int adv = nthr * 2;
-    for (int c = tid; c < nchunks; c += nthr) {
-        const int32_t a = sp_ldg(st.info + (size_t)tile_puzzle[j] * S + r0);
-        int jj = j, rr = r0 + 1;
-        if (rr >= S) { rr = 0; jj++; }
-        const int32_t b = sp_ldg(st.info + (size_t)tile_puzzle[jj] * S + rr);
         sp_st4(reinterpret_cast<int32_t*>(out_tile + 2 * (size_t)c), a, a >> 31, b, b >> 31);
-        r0 += adv;
-        while (r0 >= S) { r0 -= S; j++; }
     }
     if ((total & 1) && tid == 0) {
         const int e = total - 1, jj = e / S, rr = e - jj * S;
         out_tile[e] = sp_ldg(st.info + (size_t)tile_puzzle[jj] * S + rr);
     }
+}
+
+// shared-memory words a tile of `tile` envs needs: dyn | tile_puzzle | flat | cflat | zflat
+SPARC_HD int tile_smem_words(const StoreDev& st, int tile) {
+    return tile * (SPARC_DYN_STRIDE + 1) + ((tile * st.L + 31) >> 5) + ((tile * 4 * st.S + 31) >> 5) + ((tile * st.S + 31) >> 5) + 3;
+}
+// whole encoder for one tile; `sync` is __syncthreads on the device
+SPARC_HD void encode_tile_stage1(const StoreDev& st, uint32_t* smem, int tile, int nE, const SparcObsOut& obs, int tid, int nthr) {
+    uint32_t* dyn = smem;
+    uint32_t* tile_puzzle = dyn + tile * SPARC_DYN_STRIDE;
+    uint32_t* flat = tile_puzzle + tile;
+    uint32_t* cflat = flat + ((tile * st.L + 31) >> 5) + 1;
+    uint32_t* zflat = cflat + ((tile * 4 * st.S + 31) >> 5) + 1;
+    if (obs.base_dev) build_flat(PlaneSrc{st, dyn, tile_puzzle}, flat, nE, st.L, st.W, st.inv_L, tid, nthr);
+    if (obs.color_dev) build_flat(ColorSrc{st, tile_puzzle}, cflat, nE, 4 * st.S, st.Wc, st.inv_4S, tid, nthr);
+    if (obs.info_dev) build_flat(InfoNzSrc{st, tile_puzzle}, zflat, nE, st.S, st.nv, st.inv_S, tid, nthr);
+}
+SPARC_HD void encode_tile_stage2(const StoreDev& st, const uint32_t* smem, int tile, int nE, long long env0,
+                                 const SparcObsOut& obs, int tid, int nthr) {
+    const uint32_t* tile_puzzle = smem + tile * SPARC_DYN_STRIDE;
+    const uint32_t* flat = tile_puzzle + tile;
+    const uint32_t* cflat = flat + ((tile * st.L + 31) >> 5) + 1;
+    const uint32_t* zflat = cflat + ((tile * 4 * st.S + 31) >> 5) + 1;
+    if (obs.base_dev) expand_flat(flat, obs.base_dev + (size_t)env0 * st.L, nE * st.L, tid, nthr);
+    if (obs.color_dev) expand_color(cflat, obs.color_dev + (size_t)env0 * st.S, nE * st.S, tid, nthr);
+    if (obs.info_dev) expand_info(st, zflat, tile_puzzle, obs.info_dev + (size_t)env0 * st.S, nE, tid, nthr);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -197,6 +197,7 @@ def gen_puzzle(w, h, seed, rules=None, *, start=None, end=None, extra_solutions=
     cells_out = []   # (x, y, properties) for typed cells
     shapes = {}      # str(id) -> array
     any_poly = False
+    n_poly_regions = n_poly_pieces = n_ylop_pairs = 0
     for cells in regions:
         free = [cells[i] for i in rng.permutation(len(cells))]
         used_colors = set()
@@ -204,11 +205,18 @@ def gen_puzzle(w, h, seed, rules=None, *, start=None, end=None, extra_solutions=
         def take():
             return free.pop() if free else None
 
-        # polyomino partition first (needs one symbol cell per piece)
-        if rules.get("polys") and rng.random() < 0.6:
+        # polyomino partition first (needs one symbol cell per piece).  Density follows
+        # Witness-style puzzles: a few shapes per puzzle, not a tiling of the whole board
+        # (rules: poly_regions / poly_pieces / ylop_pairs caps per puzzle).
+        if rules.get("polys") and n_poly_regions < int(rules.get("poly_regions", 2)) and rng.random() < 0.6:
             pieces = _partition_polyominoes(cells, rng)
-            extra = 2 if (rules.get("ylops") and rng.random() < 0.5) else 0
-            if len(pieces) + extra <= len(free):
+            extra = 2 if (rules.get("ylops") and n_ylop_pairs < int(rules.get("ylop_pairs", 1))
+                          and rng.random() < 0.5) else 0
+            if len(pieces) + extra <= len(free) and \
+                    n_poly_pieces + len(pieces) + extra // 2 <= int(rules.get("poly_pieces", 6)):
+                n_poly_regions += 1
+                n_poly_pieces += len(pieces) + extra // 2
+                n_ylop_pairs += extra // 2
                 for piece in pieces:
                     arr = _shape_array(piece)
                     sid = shape_id(arr)

@@ -167,6 +167,8 @@ class PuzzleStore:
         self.static_bits = np.zeros((n, self.words_per_puzzle), np.uint32)
         self.color = np.zeros((n, SX, SY), np.uint8)
         self.info = np.zeros((n, SX, SY), np.int32)
+        self.color4 = np.zeros((n, (4 * S + 31) // 32), np.uint32)   # 4-bit colour ids, dense slab order
+        self.info_nz = np.zeros((n, (S + 31) // 32), np.uint32)      # additional_info != 0
         shapes = []
         trie = _Trie()
         self.id_to_index = {}
@@ -223,6 +225,10 @@ class PuzzleStore:
             if pz.info.min() < -2 ** 31 or pz.info.max() >= 2 ** 31:
                 raise ValueError("additional_info does not fit int32")
             self.info[i, :X, :Y] = pz.info
+            idx = np.nonzero(self.color[i].ravel())[0]
+            np.bitwise_or.at(self.color4[i], idx >> 3, self.color[i].ravel()[idx].astype(np.uint32) << ((idx & 7) * 4).astype(np.uint32))
+            idx = np.nonzero(self.info[i].ravel())[0]
+            np.bitwise_or.at(self.info_nz[i], idx >> 5, np.uint32(1) << (idx & 31).astype(np.uint32))
 
             # rule-cell boards (SG.py:456-482, 534-614)
             cb = self.cell_boards[i]
@@ -271,7 +277,12 @@ class PuzzleStore:
             if n_ylops > MAX_YLOPS:
                 raise ValueError(f"puzzle {pz.id}: more than {MAX_YLOPS} ylop instances")
             hdr["n_shapes"] = len(slots)
-            shapes.extend(slots.values())
+            if slots or cb[CB_STAR] or cb[CB_SQUARE]:
+                hdr["flags"] |= 2           # some region rule (squares / stars / shapes) can fail
+            # biggest shapes first: the exact-fit search tries slots in this order, and placing
+            # the rigid pieces early finds tilings (or dead ends) much sooner.  The answer does
+            # not depend on the order (the reference's own order is by dataset position).
+            shapes.extend(sorted(slots.values(), key=lambda r: -int(r["area"])))
 
         self.shapes = np.array(shapes, SHAPE_DTYPE) if shapes else np.zeros(1, SHAPE_DTYPE)
         self.n_shapes_total = len(shapes)

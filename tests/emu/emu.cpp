@@ -5,16 +5,20 @@
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
+#define SPARC_EMU_COUNTERS 1
 #include "../../sparc_gym_b200/csrc/sparc_core.cuh"
 
 static StoreDev make_store(const SparcStoreDesc* d) {
     StoreDev s;
     s.n_puzzles = d->n_puzzles; s.SX = d->slab_x; s.SY = d->slab_y; s.S = s.SX * s.SY;
     s.P = d->n_planes; s.L = s.P * s.S; s.W = (s.L + 31) / 32;
-    s.Wpad = (s.W + 1 > 9 ? s.W + 1 : 9) | 1;
     s.nv = (s.S + 31) / 32;
+    s.inv_L = (uint32_t)((1ull << 32) / (uint64_t)s.L) + 1u;
+    s.inv_S = (uint32_t)((1ull << 32) / (uint64_t)s.S) + 1u;
+    s.inv_4S = (uint32_t)((1ull << 32) / (uint64_t)(4 * s.S)) + 1u;
+    s.Wc = (4 * s.S + 31) / 32;
     s.hdr = d->headers; s.nb = d->node_boards; s.cb = d->cell_boards; s.sbits = d->static_bits;
-    s.color = d->color; s.info = d->info; s.shapes = d->shapes; s.trie = d->trie;
+    s.color4 = d->color4; s.info_nz = d->info_nz; s.info = d->info; s.shapes = d->shapes; s.trie = d->trie;
     return s;
 }
 
@@ -36,25 +40,21 @@ int emu_launch(const SparcStoreDesc* desc, uint32_t* core, uint32_t* vis, int32_
     if (out) p.out = *out;
     if (obs) p.obs = *obs;
     const StoreDev& st = p.st;
-    std::vector<uint32_t> smem((size_t)tile * st.Wpad + tile + 16, 0xDEADBEEFu);
+    std::vector<uint32_t> smem((size_t)tile_smem_words(st, tile) + 4, 0xDEADBEEFu);
     std::vector<EnvRegs> regs(tile);
     for (long long env0 = 0; env0 < n_envs; env0 += tile) {
         const int nE = (int)((n_envs - env0) < tile ? (n_envs - env0) : tile);
-        uint32_t* rows = smem.data();
-        uint32_t* tile_puzzle = rows + (size_t)tile * st.Wpad;
+        uint32_t* dyn = smem.data();
+        uint32_t* tile_puzzle = dyn + (size_t)tile * SPARC_DYN_STRIDE;
         for (int tid = 0; tid < nE; tid++) {
             unsigned long long my[SPARC_N_STATS];
-            if (phase_a(p, env0 + tid, regs[tid], rows + tid * st.Wpad, my) && mode == 0)
+            if (phase_a(p, env0 + tid, regs[tid], dyn + tid * SPARC_DYN_STRIDE, my) && mode == 0)
                 for (int k = 0; k < SPARC_N_STATS; k++) stats[k] += my[k];
             tile_puzzle[tid] = regs[tid].puzzle;
+            write_dyn(st, dyn, tid, regs[tid]);
         }
-        if (p.obs.base_dev) {
-            for (int tid = 0; tid < nthr; tid++) stage_static(st, rows, tile_puzzle, nE, tid, nthr);
-            for (int tid = 0; tid < nE; tid++) stage_dynamic(st, rows, tid, regs[tid]);
-            for (int tid = 0; tid < nthr; tid++) expand_base(st, rows, p.obs.base_dev + (size_t)env0 * st.L, nE, tid, nthr);
-        }
-        if (p.obs.color_dev) for (int tid = 0; tid < nthr; tid++) expand_color(st, tile_puzzle, p.obs.color_dev + (size_t)env0 * st.S, nE, tid, nthr);
-        if (p.obs.info_dev) for (int tid = 0; tid < nthr; tid++) expand_info(st, tile_puzzle, p.obs.info_dev + (size_t)env0 * st.S, nE, tid, nthr);
+        for (int tid = 0; tid < nthr; tid++) encode_tile_stage1(st, dyn, tile, nE, p.obs, tid, nthr);
+        for (int tid = 0; tid < nthr; tid++) encode_tile_stage2(st, dyn, tile, nE, env0, p.obs, tid, nthr);
     }
     return 0;
 }
@@ -74,6 +74,21 @@ int emu_validate(const SparcStoreDesc* desc, uint32_t* core, uint32_t* vis, int3
         flags[i] = (uint16_t)(validate_env(st, e.puzzle, vd, e.x, e.y, rm) | SPARC_RULE_VALID);
     }
     return 0;
+}
+
+// direct access to the two exact-fit searches (which: 0 = sweep used by the kernels, 1 = reference order)
+int emu_exact_fit(int which, uint64_t region, int w, int h, const SparcShape* shapes, int ns,
+                  const uint8_t* n_poly, const uint8_t* n_ylop, long long* iters) {
+    g_fit_iters = 0;
+    const bool ok = which ? exact_fit_reference_order(region, w, h, shapes, ns, n_poly, n_ylop)
+                          : exact_fit(region, w, h, shapes, ns, n_poly, n_ylop);
+    if (iters) *iters = g_fit_iters;
+    return ok ? 1 : 0;
+}
+long long emu_fit_iters(int reset) { long long v = g_fit_iters; if (reset) g_fit_iters = 0; return v; }
+void emu_fit_counters(long long* out3, int reset) {
+    out3[0] = g_fit_iters; out3[1] = g_fit_calls; out3[2] = g_fit_max;
+    if (reset) { g_fit_iters = g_fit_calls = g_fit_max = 0; }
 }
 
 }  // extern "C"

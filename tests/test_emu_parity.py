@@ -60,3 +60,26 @@ def test_autoreset_next_step_cycles_puzzles():
     env, orc = run_lockstep(EmuVecEnv, rows, 10, 120, False, 25, "next_step", "terminal", seed=9, follow=0.3)
     st = env.stats()
     assert st[0] > 10 and st[4] > 0          # episodes finished, steps counted
+
+
+def test_encoder_is_tiling_invariant_and_handles_tiny_lattices():
+    """Same envs, different CTA tilings / thread counts (incl. ragged last tiles and a 3x3
+    lattice whose planes are shorter than one 32-bit word) -> identical arrays, all checked
+    against the oracle."""
+    for rows in ([gen_puzzle(1, 1, s, RULES_GAPS_DOTS) for s in range(3)],
+                 gen_pool(5, [(1, 2), (2, 1), (3, 3)], RULES_FULL, seed0=70)):
+        N, T = 37, 12
+        ref = None
+        for tile, nthr in ((4, 32), (8, 128), (32, 128), (128, 128), (64, 96)):
+            env = EmuVecEnv(rows, N, traceback=True, max_steps=9, autoreset_mode="next_step", validate="terminal",
+                            tile=tile, nthr=nthr)
+            orc = OracleLockstep(rows, N, env.store.plane_keys, (env.store.slab_x, env.store.slab_y), True, 9,
+                                 autoreset_mode="next_step")
+            exp = orc.reset()
+            out = env.reset()
+            compare((out[0], env.reward, env.terminated, env.truncated, out[1]), exp, f"reset tile={tile}")
+            rng = np.random.default_rng(5)
+            for t in range(T):
+                a = rng.integers(0, 4, N).astype(np.uint8)
+                orc.step(a)
+                compare(env.step(a), orc.expected(), f"tile={tile} step {t}")

@@ -1,0 +1,141 @@
+"""The kernels' exact-fit search (one sweep over the cells, sparc_core.cuh `exact_fit`) against
+(a) the reference's own answers (golden polyfit vectors), (b) the oracle's restatement of the
+reference's search and (c) the reference-order search compiled from the same header -- on
+stamped regions with stacked / off-region ylops, duplicates, zero-area and oversized shapes."""
+import ctypes as C
+import gzip
+import json
+import os
+
+import numpy as np
+import pytest
+
+import sparc_oracle as so
+from emu.emu_env import build_emu
+from fuzzrows import SMALL_SHAPES
+from sparc_gym_b200.store import SHAPE_DTYPE, shape_slot
+
+LIB = C.CDLL(build_emu())
+LIB.emu_exact_fit.argtypes = [C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                              C.POINTER(C.c_longlong)]
+
+
+def device_fit(which, X, Y, region, polys, ylops):
+    """polys / ylops: lists of shape arrays.  Returns (bool, search iterations)."""
+    names = {}
+    for a in polys + ylops:
+        names.setdefault(json.dumps(a), len(names))
+    slots = np.zeros(max(len(names), 1), SHAPE_DTYPE)
+    for k, i in names.items():
+        slots[i] = shape_slot(json.loads(k))
+    npoly = np.zeros(32, np.uint8)
+    nylop = np.zeros(32, np.uint8)
+    for a in polys:
+        npoly[names[json.dumps(a)]] += 1
+    for a in ylops:
+        nylop[names[json.dumps(a)]] += 1
+    reg = 0
+    for (x, y) in region:
+        reg |= 1 << ((x // 2) * 8 + (y // 2))
+    it = C.c_longlong()
+    ok = LIB.emu_exact_fit(which, C.c_uint64(reg), (X - 1) // 2, (Y - 1) // 2, slots.ctypes.data, len(names),
+                           npoly.ctypes.data, nylop.ctypes.data, C.byref(it))
+    return bool(ok), it.value
+
+
+def area(a):
+    return int(np.array(a).sum())
+
+
+def test_golden_polyfit_cases():
+    with gzip.open(os.path.join(os.path.dirname(__file__), "golden", "polyfit.json.gz")) as f:
+        cases = json.loads(f.read())
+    n = 0
+    for i, c in enumerate(cases):
+        if not c["area_matched"]:
+            continue        # the rule never calls the search then (SG.py:696-699)
+        polys = [c["shapes"][x["name"]] for x in c["instances"] if x["kind"] == "poly"]
+        ylops = [c["shapes"][x["name"]] for x in c["instances"] if x["kind"] == "ylop"]
+        for which in (0, 1):
+            got, _ = device_fit(which, c["X"], c["Y"], c["region"], polys, ylops)
+            assert got == c["expected"], (i, which)
+        n += 1
+    assert n > 100
+
+
+def random_case(rng):
+    w, h = int(rng.integers(1, 6)), int(rng.integers(1, 6))
+    need = np.zeros((w, h), int)
+    polys, ylops = [], []
+    shapes = SMALL_SHAPES + [[[1, 1, 1, 1]], [[1, 0], [1, 0], [1, 1]], [[1] * 8]]
+    for _ in range(int(rng.integers(1, 6))):
+        a = np.array(shapes[int(rng.integers(len(shapes)))])
+        if a.shape[0] > w or a.shape[1] > h:
+            continue
+        ox, oy = int(rng.integers(w - a.shape[0] + 1)), int(rng.integers(h - a.shape[1] + 1))
+        need[ox:ox + a.shape[0], oy:oy + a.shape[1]] += a
+        polys.append(a.tolist())
+    for _ in range(int(rng.integers(0, 4))):
+        a = np.array(shapes[int(rng.integers(5))])
+        if a.shape[0] > w or a.shape[1] > h:
+            continue
+        ox, oy = int(rng.integers(w - a.shape[0] + 1)), int(rng.integers(h - a.shape[1] + 1))
+        sub = need[ox:ox + a.shape[0], oy:oy + a.shape[1]]
+        if (sub >= a).all() and rng.random() < 0.8:
+            sub -= a
+            ylops.append(a.tolist())
+    if need.max(initial=0) > 1:
+        # the region is a set: extra layers must come from ylops, so dig the surplus out with 1x1 ylops
+        for i, j in zip(*np.nonzero(need > 1)):
+            for _ in range(need[i, j] - 1):
+                ylops.append([[1]])
+            need[i, j] = 1
+    region = [(2 * i + 1, 2 * j + 1) for i in range(w) for j in range(h) if need[i, j] > 0]
+    r = rng.random()
+    if r < 0.3 and polys:                         # area-preserving perturbations: mostly unsolvable
+        k = int(rng.integers(3))
+        if k == 0:                                # move one region cell somewhere else
+            free = [(2 * i + 1, 2 * j + 1) for i in range(w) for j in range(h) if (2 * i + 1, 2 * j + 1) not in region]
+            if free and region:
+                region[int(rng.integers(len(region)))] = free[int(rng.integers(len(free)))]
+                region.sort()
+        elif k == 1:                              # swap a poly for another shape of the same area
+            i = int(rng.integers(len(polys)))
+            same = [q for q in shapes if area(q) == area(polys[i]) and q != polys[i]]
+            if same:
+                polys[i] = same[int(rng.integers(len(same)))]
+        else:                                     # swap a ylop likewise / add a cancelling pair of different shapes
+            two = [q for q in shapes if area(q) == 2]
+            polys.append(two[0]); ylops.append(two[1])
+    elif r < 0.4 and polys:                       # area-breaking (filtered out unless it happens to match)
+        k = int(rng.integers(3))
+        if k == 0 and len(region) > 1:
+            region.pop(int(rng.integers(len(region))))
+        elif k == 1:
+            polys[int(rng.integers(len(polys)))] = shapes[int(rng.integers(len(shapes)))]
+        else:
+            polys.append(shapes[int(rng.integers(3))])
+    return 2 * w + 1, 2 * h + 1, region, polys, ylops[:6]
+
+
+def test_sweep_equals_reference_order_and_oracle():
+    rng = np.random.default_rng(11)
+    n = n_fit = n_y = 0
+    worst = 0
+    while n < 1500:
+        X, Y, region, polys, ylops = random_case(rng)
+        if not region or not polys:
+            continue
+        if sum(map(area, polys)) - sum(map(area, ylops)) != len(region):
+            continue       # only area-matched cases reach the search
+        a, it_sweep = device_fit(0, X, Y, region, polys, ylops)
+        b, it_ref = device_fit(1, X, Y, region, polys, ylops)
+        assert a == b, (X, Y, region, polys, ylops)
+        if n % 6 == 0 and len(ylops) <= 2:      # the Python search is slow: sample it
+            want = so.exact_fit(X, Y, region, [(json.dumps(p), p) for p in polys], [(json.dumps(p), p) for p in ylops])
+            assert a == want, (X, Y, region, polys, ylops)
+        n += 1
+        n_fit += a
+        n_y += bool(ylops)
+        worst = max(worst, it_sweep)
+    assert n_fit > 300 and n - n_fit > 100 and n_y > 300, (n_fit, n_y, worst)
