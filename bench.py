@@ -138,6 +138,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--validate", default="terminal")
     ap.add_argument("--autoreset", default="same_step")
+    ap.add_argument("--no-obs", action="store_true", help="diagnostic: skip the observation rewrite (dynamics only)")
     ap.add_argument("--no-graph", action="store_true", help="launch every step from Python instead of one CUDA graph of K steps")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
@@ -179,7 +180,7 @@ def main():
     t_build = time.perf_counter()
     rows = config_pool(cfg, n_puzzles=pool_n)
     env = SparcVecEnv(rows, n_env, traceback=traceback, max_steps=max_steps, autoreset_mode=args.autoreset,
-                      puzzle_stride=1, validate=args.validate, device=dev)
+                      puzzle_stride=1, validate=args.validate, device=dev, write_obs=not args.no_obs)
     st = env.store
     t_build = time.perf_counter() - t_build
     K, W = args.steps, args.warmup

@@ -41,6 +41,8 @@ struct SparcEnv {
     StepCfg cfg;
     StateDev s;
     int tile;                // envs per CTA
+    int ring_grid;           // >0: use k_env_ring with this many persistent CTAs (one per SM)
+    unsigned int* sched;     // [2] tile counter + finished-producer counter of k_env_ring
     int64_t launches;
     uint8_t* act_stage;      // device staging for the *_host call
     float* rew_stage;
@@ -48,41 +50,272 @@ struct SparcEnv {
     uint8_t* trunc_stage;
 };
 
-// dynamic shared (tile_smem_words): dyn[tile][9] | tile_puzzle[tile] | flat | cflat | zflat
-extern __shared__ uint32_t smem[];
+// dynamic shared memory of both kernels: tile heads (dyn rows + puzzle ids) | flat strings
+extern __shared__ __align__(128) uint32_t smem[];
 
+__device__ __forceinline__ void reduce_stats(const KParams& p, bool have, const unsigned long long* my) {
+#pragma unroll
+    for (int k = 0; k < SPARC_N_STATS; k++) {                 // warp-reduce, one atomic per counter per warp
+        unsigned long long v = have ? my[k] : 0ull;
+#pragma unroll
+        for (int off = 16; off; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(p.sd.stats + k, v);
+    }
+}
+
+// ---- simple kernel: one CTA = one tile (small batches: every CTA is resident at once) ----------
 __global__ void __launch_bounds__(CTA_THREADS, SPARC_MINBLOCKS) k_env(const KParams p) {
     const StoreDev& st = p.st;
     const int tid = threadIdx.x;
     const long long env0 = (long long)blockIdx.x * p.tile;
     const long long n = p.cfg.n_envs;
     const int nE = (int)min((long long)p.tile, n - env0);
-    uint32_t* dyn = smem;
-    uint32_t* tile_puzzle = smem + p.tile * SPARC_DYN_STRIDE;
+    uint32_t* head = smem;
+    uint32_t* flats = smem + tile_head_words(p.tile);
 
     EnvRegs e;
     unsigned long long my_stats[SPARC_N_STATS];
     bool have_stats = false;
     if (tid < nE) {
-        have_stats = phase_a(p, env0 + tid, e, dyn + tid * SPARC_DYN_STRIDE, my_stats);
-        tile_puzzle[tid] = e.puzzle;
-        write_dyn(st, dyn, tid, e);
+        have_stats = phase_a(p, env0 + tid, e, head + tid * SPARC_DYN_STRIDE, my_stats);
+        head[p.tile * SPARC_DYN_STRIDE + tid] = e.puzzle;
+        write_dyn(st, head, tid, e);
     }
-    // statistics: warp-reduce, one atomic per counter per warp (the dynamics threads are the first warps)
-    if (p.mode == 0 && tid < ((nE + 31) & ~31)) {
-#pragma unroll
-        for (int k = 0; k < SPARC_N_STATS; k++) {
-            unsigned long long v = have_stats ? my_stats[k] : 0ull;
-#pragma unroll
-            for (int off = 16; off; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
-            if ((tid & 31) == 0 && v) atomicAdd(p.sd.stats + k, v);
-        }
-    }
+    if (p.mode == 0 && tid < ((nE + 31) & ~31)) reduce_stats(p, have_stats, my_stats);
     if (!p.obs.base_dev && !p.obs.color_dev && !p.obs.info_dev) return;
     __syncthreads();
-    encode_tile_stage1(st, smem, p.tile, nE, p.obs, tid, CTA_THREADS);
+    encode_tile_stage1a(st, head, flats, p.tile, nE, p.obs, tid, CTA_THREADS);
     __syncthreads();
-    encode_tile_stage2(st, smem, p.tile, nE, env0, p.obs, tid, CTA_THREADS);
+    encode_tile_stage1b(st, head, flats, p.tile, nE, p.obs, tid, CTA_THREADS);
+    __syncthreads();
+    encode_tile_stage2(st, head, flats, p.tile, nE, env0, p.obs, tid, CTA_THREADS);
+}
+
+// ---- ring kernel: one persistent, warp-specialised CTA per SM -------------------------------------
+// RING_PROD producer warps each own one shared-memory slot.  A producer takes the next tile of
+// 32 envs from a global counter, runs the latency-bound part (dynamics, terminal validation,
+// autoreset: one env per lane) and packs the tile's observation into the slot's flat bit strings;
+// RING_CONS consumer warps visit the slots round-robin and do nothing but turn bit strings into
+// coalesced 16-byte streaming stores.  Hand-off is by mbarriers (full / empty per slot).
+//
+// Why one fat CTA per SM instead of many thin ones: (1) the store path of an SM is only busy
+// while some warp is in the expand loop, so the dependent-load chains must run *beside* it, not
+// in front of it; (2) HBM write efficiency depends on how much memory is being written at once --
+// tools/wpattern.cu measures 7.2 TB/s when the chip-wide window of open tiles is ~40 MB and
+// 6.5 TB/s at 166-330 MB (1184 thin CTAs x 140-281 KB); 148 CTAs x 281 KB keeps it at 41 MB.
+#ifndef RING_PROD
+#define RING_PROD 8
+#endif
+#ifndef RING_CONS
+#define RING_CONS 8
+#endif
+#define RING_THREADS ((RING_PROD + RING_CONS) * 32)
+#define RING_TILE 32
+#define RING_END 0xFFFFFFFFu
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+
+// ---- consumer side of the ring kernel: expand into a shared staging block, then hand the block to
+// the TMA engine (cp.async.bulk shared -> global).  Global stores issued through the LSU
+// (st.global) fill the SM's load/store queue and every load of the producer warps queues up behind
+// them (measured: the producers' dependent-load chains ran ~5x slower next to an st.global stream);
+// bulk stores keep the LSU free for the producers.
+#define STAGE_CHUNKS 256                         // 16-byte chunks per staging block (4 KB)
+#define STAGE_WORDS (STAGE_CHUNKS * 4)
+__device__ __forceinline__ void tma_store(void* gdst, const void* ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// One warp writes its share of a stream: blocks of STAGE_CHUNKS chunks, block b by warp b mod nw.
+// `fill(c)` returns the 16 bytes of chunk c.  stage: 2 x STAGE_WORDS words private to the warp.
+template <class Fill>
+__device__ __forceinline__ void stream_blocks(char* gbase, int nchunks, int wc, int nw, int lane, uint32_t* stage,
+                                              uint32_t& phase, const Fill& fill) {
+    for (int b0 = wc * STAGE_CHUNKS; b0 < nchunks; b0 += nw * STAGE_CHUNKS) {
+        uint32_t* buf = stage + (phase & 1u) * STAGE_WORDS;
+        if (lane == 0) tma_wait_read_1();                     // the block sent two rounds ago has left this buffer
+        __syncwarp();
+        const int cnt = min(STAGE_CHUNKS, nchunks - b0);
+#pragma unroll
+        for (int it = 0; it < STAGE_CHUNKS / 32; it++) {
+            const int q = it * 32 + lane;
+            if (q < cnt) reinterpret_cast<int4*>(buf)[q] = fill(b0 + q);
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) tma_store(gbase + (size_t)b0 * 16, buf, (uint32_t)cnt * 16u);
+        phase++;
+    }
+}
+
+__device__ __forceinline__ void ring_expand_tile(const StoreDev& st, const uint32_t* head, const uint32_t* flats, int nE,
+                                                 long long env0, const SparcObsOut& obs, int wc, int nw, int lane,
+                                                 uint32_t* stage, uint32_t& phase) {
+    const uint32_t* tile_puzzle = head + RING_TILE * SPARC_DYN_STRIDE;
+    const uint32_t* rb = flats;
+    const uint32_t* rc = rb + RING_TILE * (st.W + 2);
+    const uint32_t* rz = rc + RING_TILE * (st.Wc + 2);
+    if (obs.base_dev) {
+        const int L = st.L, Ws = st.W + 2, total = nE * L;
+        int32_t* out = obs.base_dev + (size_t)env0 * L;
+        stream_blocks(reinterpret_cast<char*>(out), total >> 2, wc, nw, lane, stage, phase, [&](int c) {
+            const uint32_t n = row_fetch(rb, 4u * (uint32_t)c, L, Ws, st.inv_L);
+            return make_int4(n & 1, (n >> 1) & 1, (n >> 2) & 1, (n >> 3) & 1);
+        });
+        if (wc == 0) for (int e = (total & ~3) + lane; e < total; e += 32) out[e] = row_fetch(rb, (uint32_t)e, L, Ws, st.inv_L) & 1u;
+    }
+    if (obs.color_dev) {
+        const int L = 4 * st.S, Ws = st.Wc + 2, total = nE * st.S;
+        int32_t* out = obs.color_dev + (size_t)env0 * st.S;
+        stream_blocks(reinterpret_cast<char*>(out), total >> 2, wc, nw, lane, stage, phase, [&](int c) {
+            const uint32_t n = row_fetch(rc, 16u * (uint32_t)c, L, Ws, st.inv_4S);
+            return make_int4(n & 15, (n >> 4) & 15, (n >> 8) & 15, (n >> 12) & 15);
+        });
+        if (wc == 0) for (int e = (total & ~3) + lane; e < total; e += 32) out[e] = row_fetch(rc, 4u * (uint32_t)e, L, Ws, st.inv_4S) & 15u;
+    }
+    if (obs.info_dev) {
+        const int S = st.S, Ws = st.nv + 2, total = nE * S;
+        int64_t* out = obs.info_dev + (size_t)env0 * S;
+        stream_blocks(reinterpret_cast<char*>(out), total >> 1, wc, nw, lane, stage, phase, [&](int c) {
+            const uint32_t e0 = 2u * (uint32_t)c;
+            const uint32_t m = row_fetch(rz, e0, S, Ws, st.inv_S) & 3u;
+            int32_t a = 0, b = 0;
+            if (m) {
+                const int j = (int)__umulhi(e0, st.inv_S), r = (int)e0 - j * S;
+                if (m & 1) a = __ldg(st.info + (size_t)tile_puzzle[j] * S + r);
+                if (m & 2) {
+                    const int j2 = (r + 1 >= S) ? j + 1 : j, r2 = (r + 1 >= S) ? 0 : r + 1;
+                    b = __ldg(st.info + (size_t)tile_puzzle[j2] * S + r2);
+                }
+            }
+            return make_int4(a, a >> 31, b, b >> 31);
+        });
+        if ((total & 1) && wc == 0 && lane == 0) {
+            const int e = total - 1, jj = e / S, rr = e - jj * S;
+            out[e] = __ldg(st.info + (size_t)tile_puzzle[jj] * S + rr);
+        }
+    }
+}
+
+__host__ __device__ inline int ring_slot_words(const StoreDev& st) {
+    return (tile_head_words(RING_TILE) + 1 + tile_flat_words(st, RING_TILE) + 3) & ~3;   // keeps the staging blocks 16-byte aligned
+}
+
+__global__ void __launch_bounds__(RING_THREADS, 1) k_env_ring(const KParams p, unsigned int* sched) {
+    const StoreDev& st = p.st;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long n = p.cfg.n_envs;
+    const unsigned ntiles = (unsigned)((n + RING_TILE - 1) / RING_TILE);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);              // [RING_PROD]
+    uint64_t* empty = full + RING_PROD;                              // [RING_PROD]
+    uint32_t* slots = smem + 4 * RING_PROD;
+    const int slot_words = ring_slot_words(st);
+    const int hw = tile_head_words(RING_TILE);
+    if (tid == 0) {
+        for (int w = 0; w < RING_PROD; w++) { mbar_init(full + w, 1); mbar_init(empty + w, RING_CONS); }
+    }
+    __syncthreads();
+#ifdef RING_PROFILE
+    long long t_wait = 0, t_a = 0, t_b = 0, t_c = 0, t0;
+#define TICK() (t0 = clock64())
+#define TOCK(acc) (acc += clock64() - t0)
+#else
+#define TICK() ((void)0)
+#define TOCK(acc) ((void)0)
+#endif
+    if (warp < RING_PROD) {                                          // ------------------- producers
+        uint32_t* head = slots + (size_t)warp * slot_words;
+        uint32_t* flats = head + hw + 1;
+        for (uint32_t r = 0;; r++) {
+            TICK();
+            if (r > 0) mbar_wait(empty + warp, (r - 1) & 1);         // the consumers drained round r-1
+            TOCK(t_wait);
+            unsigned t = 0;
+            if (lane == 0) t = atomicAdd(sched, 1u);
+            t = __shfl_sync(0xffffffffu, t, 0);
+            if (t >= ntiles) {
+                if (lane == 0) { head[hw] = RING_END; mbar_arrive(full + warp); }
+                break;
+            }
+            const long long env0 = (long long)t * RING_TILE;
+            const int nE = (int)min((long long)RING_TILE, n - env0);
+            EnvRegs e;
+            unsigned long long my_stats[SPARC_N_STATS];
+            bool have_stats = false;
+            TICK();
+            if (lane < nE) {
+                prefetch_static(st, p.sd.core[4 * (env0 + lane)]);   // encoder inputs arrive while the dynamics run
+                have_stats = phase_a(p, env0 + lane, e, head + lane * SPARC_DYN_STRIDE, my_stats);
+                head[RING_TILE * SPARC_DYN_STRIDE + lane] = e.puzzle;
+                write_dyn(st, head, lane, e);
+            }
+            if (p.mode == 0) reduce_stats(p, have_stats, my_stats);
+            __syncwarp();
+            TOCK(t_a);
+            TICK();
+            encode_tile_stage1a(st, head, flats, RING_TILE, nE, p.obs, lane, 32);
+            __syncwarp();
+            encode_tile_stage1b(st, head, flats, RING_TILE, nE, p.obs, lane, 32);
+            __syncwarp();
+            TOCK(t_b);
+            if (lane == 0) { head[hw] = t; mbar_arrive(full + warp); }   // release: slot contents visible
+        }
+#ifdef RING_PROFILE
+        if (lane == 0) { atomicAdd((unsigned long long*)(sched + 2), (unsigned long long)t_wait); atomicAdd((unsigned long long*)(sched + 4), (unsigned long long)t_a); atomicAdd((unsigned long long*)(sched + 6), (unsigned long long)t_b); }
+#endif
+        if (lane == 0) {                                             // last producer of the grid re-arms the scheduler
+            __threadfence();
+            if (atomicAdd(sched + 1, 1u) == gridDim.x * RING_PROD - 1) { sched[0] = 0; sched[1] = 0; __threadfence(); }
+        }
+    } else {                                                         // ------------------- consumers
+        const int wc = warp - RING_PROD;
+        uint32_t* stage = slots + (size_t)RING_PROD * slot_words + (size_t)wc * 2 * STAGE_WORDS;
+        uint32_t parity = 0, done = 0, stage_phase = 0;
+        const uint32_t all = (1u << RING_PROD) - 1u;
+        for (int w = 0; done != all; w = (w + 1 == RING_PROD) ? 0 : w + 1) {
+            if ((done >> w) & 1u) continue;
+            const uint32_t* head = slots + (size_t)w * slot_words;
+            TICK();
+            mbar_wait(full + w, (parity >> w) & 1u);
+            TOCK(t_wait);
+            parity ^= 1u << w;
+            const uint32_t t = head[hw];
+            if (t == RING_END) { done |= 1u << w; continue; }
+            const long long env0 = (long long)t * RING_TILE;
+            const int nE = (int)min((long long)RING_TILE, n - env0);
+            TICK();
+#ifdef RING_TMA_STORE
+            ring_expand_tile(st, head, head + hw + 1, nE, env0, p.obs, wc, RING_CONS, lane, stage, stage_phase);
+#else
+            (void)stage; (void)stage_phase;
+            encode_tile_stage2(st, head, head + hw + 1, RING_TILE, nE, env0, p.obs, tid - RING_PROD * 32, RING_CONS * 32);
+#endif
+            __syncwarp();
+            TOCK(t_c);
+            if (lane == 0) mbar_arrive(empty + w);                   // (the rows were read into the staging blocks)
+        }
+        if (lane == 0) tma_wait_all();                               // bulk stores must drain before the CTA retires
+#ifdef RING_PROFILE
+        if (lane == 0) { atomicAdd((unsigned long long*)(sched + 8), (unsigned long long)t_wait); atomicAdd((unsigned long long*)(sched + 10), (unsigned long long)t_c); }
+#endif
+    }
 }
 
 // stand-alone validator (SG.py:941-950) for sparc_validate: one env per thread
@@ -155,6 +388,9 @@ int sparc_store_create(const SparcStoreDesc* desc, int device, SparcStore** out)
     d.inv_S = (uint32_t)((1ull << 32) / (uint64_t)d.S) + 1u;
     d.inv_4S = (uint32_t)((1ull << 32) / (uint64_t)(4 * d.S)) + 1u;
     d.Wc = (4 * d.S + 31) / 32;
+    d.inv_wsb = (uint32_t)((1ull << 32) / (uint64_t)(d.W + 2)) + 1u;
+    d.inv_wsc = (uint32_t)((1ull << 32) / (uint64_t)(d.Wc + 2)) + 1u;
+    d.inv_wsz = (uint32_t)((1ull << 32) / (uint64_t)(d.nv + 2)) + 1u;
     memcpy(s->plane_ids, desc->plane_ids, sizeof(s->plane_ids));
     const size_t n = desc->n_puzzles;
     int rc;
@@ -199,6 +435,27 @@ int sparc_env_create(SparcStore* store, int64_t n_envs, int traceback, int max_s
     e->cfg.n_envs = n_envs; e->cfg.traceback = traceback != 0; e->cfg.max_steps = max_steps;
     e->cfg.autoreset = autoreset_mode; e->cfg.stride = puzzle_stride; e->cfg.validate_mode = validate_mode;
     e->tile = pick_tile(n_envs);
+    {   // tiles above ~100 envs need more than the default 48 KB of dynamic shared memory
+        const size_t shmem = (size_t)(tile_head_words(e->tile) + tile_flat_words(store->d, e->tile)) * sizeof(uint32_t);
+        if (shmem > 48 * 1024) {
+            cudaError_t ae = cudaFuncSetAttribute(k_env, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem);
+            if (ae != cudaSuccess) { delete e; return fail(SPARC_E_CUDA, "k_env shared memory: %s", cudaGetErrorString(ae)); }
+        }
+    }
+    {   // big batches: the ring kernel, one persistent CTA per SM
+        int dev_sms = 0;
+        cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, store->device);
+        const char* pe = getenv("SPARC_RING");
+        const int want = pe ? atoi(pe) : -1;                  // 0 = never, 1 = always, unset = automatic
+        const size_t shmem = (size_t)(4 * RING_PROD + RING_PROD * ring_slot_words(store->d) + RING_CONS * 2 * STAGE_WORDS) * sizeof(uint32_t);
+        const int64_t ntiles = (n_envs + RING_TILE - 1) / RING_TILE;
+        (void)ntiles;
+        if (want == 1) {      // opt-in: measured on par with the one-tile-per-CTA kernel so far (kernel notes)
+            cudaError_t ae = cudaFuncSetAttribute(k_env_ring, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem);
+            if (ae != cudaSuccess) { delete e; return fail(SPARC_E_CUDA, "ring kernel shared memory: %s", cudaGetErrorString(ae)); }
+            e->ring_grid = (int)(ntiles < dev_sms ? ntiles : dev_sms);
+        }
+    }
     const size_t n = (size_t)n_envs;
     cudaError_t err = cudaSuccess;
     auto alloc = [&](void** p, size_t bytes) { if (err == cudaSuccess) { err = cudaMalloc(p, bytes); if (err == cudaSuccess) err = cudaMemset(*p, 0, bytes); } };
@@ -207,6 +464,7 @@ int sparc_env_create(SparcStore* store, int64_t n_envs, int traceback, int max_s
     alloc((void**)&e->s.ep_ret, n * 4);
     if (traceback) alloc((void**)&e->s.moves, n * SPARC_MOVE_WORDS * 4);
     alloc((void**)&e->s.stats, SPARC_N_STATS * 8);
+    alloc((void**)&e->sched, 16 * sizeof(unsigned int));   // [2..] cycle counters when built with -DRING_PROFILE
     alloc((void**)&e->act_stage, n);
     alloc((void**)&e->rew_stage, n * 4);
     alloc((void**)&e->term_stage, n);
@@ -222,7 +480,7 @@ int sparc_env_create(SparcStore* store, int64_t n_envs, int traceback, int max_s
 int sparc_env_destroy(SparcEnv* e) {
     if (!e) return SPARC_OK;
     cudaSetDevice(e->store->device);
-    void* ptrs[] = {e->s.core, e->s.vis, e->s.ep_ret, e->s.moves, e->s.stats, e->act_stage, e->rew_stage, e->term_stage, e->trunc_stage};
+    void* ptrs[] = {e->s.core, e->s.vis, e->s.ep_ret, e->s.moves, e->s.stats, e->sched, e->act_stage, e->rew_stage, e->term_stage, e->trunc_stage};
     for (void* p : ptrs) if (p) cudaFree(p);
     delete e;
     return SPARC_OK;
@@ -231,9 +489,15 @@ int sparc_env_destroy(SparcEnv* e) {
 static int launch_env(SparcEnv* e, KParams& p, void* stream) {
     p.st = e->store->d; p.sd = e->s; p.cfg = e->cfg; p.tile = e->tile;
     const int64_t n = e->cfg.n_envs;
-    const unsigned grid = (unsigned)((n + e->tile - 1) / e->tile);
-    const size_t shmem = (size_t)tile_smem_words(p.st, e->tile) * sizeof(uint32_t);
-    k_env<<<grid, CTA_THREADS, shmem, (cudaStream_t)stream>>>(p);
+    const unsigned ntiles = (unsigned)((n + e->tile - 1) / e->tile);
+    if (e->ring_grid > 0) {
+        p.tile = RING_TILE;
+        const size_t shmem = (size_t)(4 * RING_PROD + RING_PROD * ring_slot_words(p.st) + RING_CONS * 2 * STAGE_WORDS) * sizeof(uint32_t);
+        k_env_ring<<<(unsigned)e->ring_grid, RING_THREADS, shmem, (cudaStream_t)stream>>>(p, e->sched);
+    } else {
+        const size_t shmem = (size_t)(tile_head_words(e->tile) + tile_flat_words(p.st, e->tile)) * sizeof(uint32_t);
+        k_env<<<ntiles, CTA_THREADS, shmem, (cudaStream_t)stream>>>(p);
+    }
     CU(cudaGetLastError());
     e->launches++;
     return SPARC_OK;
@@ -318,6 +582,14 @@ int sparc_state_save(SparcEnv* e, void* blob_dev, void* stream) {
 int sparc_state_load(SparcEnv* e, const void* blob_dev, void* stream) {
     if (!e || !blob_dev) return fail(SPARC_E_ARG, "null argument%s");
     return state_copy(e, (char*)blob_dev, false, stream);
+}
+
+int sparc_debug_counters(SparcEnv* e, uint64_t* out5_host) {   /* RING_PROFILE builds only: producer wait / dynamics / build, consumer wait / expand cycles */
+    if (!e || !out5_host) return fail(SPARC_E_ARG, "null argument%s");
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(out5_host, e->sched + 2, 5 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    CU(cudaMemset(e->sched + 2, 0, 5 * sizeof(uint64_t)));
+    return SPARC_OK;
 }
 
 int64_t sparc_env_num_envs(const SparcEnv* e) { return e ? e->cfg.n_envs : 0; }

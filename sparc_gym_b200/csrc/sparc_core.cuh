@@ -80,6 +80,7 @@ struct StoreDev {
     int nv;                        // words of one dense plane: ceil(S/32)
     int Wc;                        // words of the 4-bit colour string: ceil(4S/32)
     uint32_t inv_L, inv_S, inv_4S; // floor(2^32/d)+1: exact x/d by one mul-hi for the x used here
+    uint32_t inv_wsb, inv_wsc, inv_wsz;   // same for the row strides W+2, Wc+2, nv+2
     const SparcPuzzleHeader* hdr;
     const uint32_t* nb;            // [n][SPARC_N_NODE_BOARDS][8]
     const uint64_t* cb;            // [n][SPARC_N_CELL_BOARDS]
@@ -631,12 +632,19 @@ SPARC_HD int validate_env(const StoreDev& st, uint32_t puzzle, const uint32_t* v
 
 // ---------------------------------------------------------------------------------------------
 // observation encoder (SG.py:956-979 with a full rewrite in the reference dtypes)
-//   tile : nE consecutive envs starting at env0 (env0 % 4 == 0 keeps every stream 16-B aligned)
-//   dyn  : shared, SPARC_DYN_STRIDE words per env: visited plane (dense, 8 words) + bit index of
-//          the agent inside the env's L-bit plane string
-//   flat : shared, the tile's one-hot planes as ONE bit string in output element order
-//          (env j occupies bits [j*L, (j+1)*L)), so that output chunk c (4 consecutive int32 of
-//          the tile's contiguous [nE][P][SX][SY] block) is simply nibble c of the string
+//
+//   tile : nE consecutive envs starting at env0 (env0 % 4 == 0 keeps every stream 16-B aligned).
+//   The tile's output is three contiguous streams (base int32[nE][P][SX][SY], colour
+//   int32[nE][SX][SY], additional_info int64[nE][SX][SY]); each is written in 16-byte chunks,
+//   chunk c by thread c mod nthr, so a warp store covers 512 contiguous bytes.
+//
+//   Shared-memory staging ("rows"): for each stream, env j's bit string (L bits: 1 bit per base
+//   element, 4 per colour element, 1 "non-zero" bit per info element) is stored in its own row,
+//   shifted left by o_j = (j*L) mod 32.  Bit g of the tile-wide stream (g = j*L + r) then sits
+//   at row-bit o_j + r, which is congruent to g mod 32: the bits of a chunk never straddle a word
+//   and one LDS + one shift fetches them.  The few bits of env j+1 that share env j's last chunk
+//   are appended to row j ("tail").
+//   dyn : SPARC_DYN_STRIDE words per env: visited plane (dense, 8 words) + bit index of the agent
 // ---------------------------------------------------------------------------------------------
 #define SPARC_DYN_STRIDE 9
 
@@ -647,92 +655,147 @@ SPARC_HD void write_dyn(const StoreDev& st, uint32_t* dyn, int j, const EnvRegs&
     row[8] = (uint32_t)(2 * st.S + e.x * st.SY + e.y);       // agent_location is plane 2
 }
 
-// bit-string sources: word k of env j's string
+// pull one puzzle's encoder inputs (plane bits, colour nibbles, info mask) towards this SM's L1
+SPARC_HD void prefetch_static(const StoreDev& st, uint32_t puzzle) {
+#if defined(__CUDA_ARCH__)
+    const char* a = reinterpret_cast<const char*>(st.sbits + (size_t)puzzle * st.W);
+    for (int off = 0; off < st.W * 4; off += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(a + off));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(a + st.W * 4 - 4));
+    const char* c = reinterpret_cast<const char*>(st.color4 + (size_t)puzzle * st.Wc);
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(c));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(c + st.Wc * 4 - 4));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(st.info_nz + (size_t)puzzle * st.nv));
+#else
+    (void)st; (void)puzzle;
+#endif
+}
+
+// bit-string sources: word k of env j's string (0 outside [0, W))
 struct PlaneSrc {                       // the P one-hot planes: static planes of the puzzle | visited (plane 0) | agent bit
     const StoreDev& st; const uint32_t* dyn; const uint32_t* tile_puzzle;
-    SPARC_HD uint32_t word(int j, int k) const {
+    SPARC_HD int L() const { return st.L; }
+    SPARC_HD int W() const { return st.W; }
+    SPARC_HD uint32_t raw(int j, int k) const {                 // the global-memory part (issued early, in batches)
+        return (unsigned)k < (unsigned)st.W ? sp_ldg(st.sbits + (size_t)tile_puzzle[j] * st.W + k) : 0u;
+    }
+    SPARC_HD uint32_t fix(int j, int k, uint32_t w) const {     // the shared-memory part
+        if ((unsigned)k >= (unsigned)st.W) return 0u;
         const uint32_t* row = dyn + j * SPARC_DYN_STRIDE;
-        uint32_t w = sp_ldg(st.sbits + (size_t)tile_puzzle[j] * st.W + k);
         if (k < st.nv) w |= row[k];
         const uint32_t ab = row[8];
         if ((int)(ab >> 5) == k) w |= 1u << (ab & 31);
         return w;
     }
+    SPARC_HD uint32_t word(int j, int k) const { return fix(j, k, raw(j, k)); }
 };
 struct ColorSrc {                       // colour plane, 4 bits per node
     const StoreDev& st; const uint32_t* tile_puzzle;
-    SPARC_HD uint32_t word(int j, int k) const { return sp_ldg(st.color4 + (size_t)tile_puzzle[j] * st.Wc + k); }
+    SPARC_HD int L() const { return 4 * st.S; }
+    SPARC_HD int W() const { return st.Wc; }
+    SPARC_HD uint32_t raw(int j, int k) const {
+        return (unsigned)k < (unsigned)st.Wc ? sp_ldg(st.color4 + (size_t)tile_puzzle[j] * st.Wc + k) : 0u;
+    }
+    SPARC_HD uint32_t fix(int, int, uint32_t w) const { return w; }
+    SPARC_HD uint32_t word(int j, int k) const { return raw(j, k); }
 };
 struct InfoNzSrc {                      // additional_info != 0, 1 bit per node
     const StoreDev& st; const uint32_t* tile_puzzle;
-    SPARC_HD uint32_t word(int j, int k) const { return sp_ldg(st.info_nz + (size_t)tile_puzzle[j] * st.nv + k); }
+    SPARC_HD int L() const { return st.S; }
+    SPARC_HD int W() const { return st.nv; }
+    SPARC_HD uint32_t raw(int j, int k) const {
+        return (unsigned)k < (unsigned)st.nv ? sp_ldg(st.info_nz + (size_t)tile_puzzle[j] * st.nv + k) : 0u;
+    }
+    SPARC_HD uint32_t fix(int, int, uint32_t w) const { return w; }
+    SPARC_HD uint32_t word(int j, int k) const { return raw(j, k); }
 };
 
-// stage 1 (cooperative): concatenate the envs' L-bit strings (W words each at the source) into
-// one flat bit string: env j occupies bits [j*L, (j+1)*L).
+// stage 1a (cooperative): rows[j][k] = env j's string shifted left by o_j, k in [0, W+1].
+// Four row words per thread per pass, all global loads issued before any is used.
 template <class Src>
-SPARC_HD void build_flat(const Src& src, uint32_t* flat, int nE, int L, int W, uint32_t inv_L, int tid, int nthr) {
-    const int nwords = (nE * L + 31) >> 5;
-    for (int f = tid; f < nwords; f += nthr) {
-        const uint32_t b = 32u * (uint32_t)f;
-        int j = (int)sp_umulhi(b, inv_L);
-        int r = (int)b - j * L;
-        uint32_t v = 0;
-        int filled = 0;
-        do {                                                    // usually 1 pass, 2 at an env boundary
-            const int k = r >> 5, sh = r & 31;
-            const uint32_t lo = src.word(j, k);
-            const uint32_t hi = (sh && k + 1 < W) ? src.word(j, k + 1) : 0u;
-            uint32_t bits = sp_funnel_r(lo, hi, sh);
-            const int nb = L - r;                               // bits env j still owns from r on
-            if (nb < 32) bits &= (1u << nb) - 1u;
-            v |= bits << filled;
-            filled += nb;
-            j++; r = 0;
-        } while (filled < 32 && j < nE);
-        flat[f] = v;
+SPARC_HD void build_rows(const Src& src, uint32_t* rows, int nE, uint32_t inv_ws, int tid, int nthr) {
+    const int L = src.L(), Ws = src.W() + 2;
+    const int total = nE * Ws;
+    for (int base = tid; base < total; base += 4 * nthr) {
+        int j[4], k[4];
+        uint32_t o[4], hi[4], lo[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int idx = base + u * nthr;
+            j[u] = (int)sp_umulhi((uint32_t)idx, inv_ws); k[u] = idx - j[u] * Ws;
+            o[u] = (uint32_t)(j[u] * L) & 31u;
+            const bool act = idx < total;
+            hi[u] = act ? src.raw(j[u], k[u]) : 0u;
+            lo[u] = (act && o[u]) ? src.raw(j[u], k[u] - 1) : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int idx = base + u * nthr;
+            if (idx < total) {
+                const uint32_t h = src.fix(j[u], k[u], hi[u]);
+                const uint32_t l = o[u] ? src.fix(j[u], k[u] - 1, lo[u]) : 0u;
+                rows[idx] = o[u] ? sp_funnel_r(l, h, 32u - o[u]) : h;   // (h << o) | (l >> (32 - o))
+            }
+        }
     }
 }
-// stage 2 (cooperative): expand bits to int32, 16 bytes per store, consecutive threads ->
-// consecutive 16-byte chunks (coalesced 512-byte warp stores)
-SPARC_HD void expand_flat(const uint32_t* flat, int32_t* out_tile, int total, int tid, int nthr) {
-    const int nchunks = total >> 2;
+// stage 1b (one thread per env, after a barrier): append to row j the first bits of env j+1 that
+// belong to env j's last chunk.  A = bits per 16-byte chunk of this stream.
+template <class Src>
+SPARC_HD void build_tails(const Src& src, uint32_t* rows, int nE, int A, int tid, int nthr) {
+    const int L = src.L(), Ws = src.W() + 2;
+    for (int j = tid; j + 1 < nE; j += nthr) {
+        const int end = (j + 1) * L;                            // first stream bit of env j+1
+        const int tb = (A - (end % A)) % A;
+        if (!tb) continue;
+        const uint32_t bits = src.word(j + 1, 0) & ((1u << tb) - 1u);
+        const int pos = ((j * L) & 31) + L;                     // row-bit right behind env j's own bits
+        rows[j * Ws + (pos >> 5)] |= bits << (pos & 31);
+    }
+}
+// stage 2 (cooperative): expand.  g = first stream bit of the chunk -> (env j, row bit)
+SPARC_HD uint32_t row_fetch(const uint32_t* rows, uint32_t g, int L, int Ws, uint32_t inv_L) {
+    const int j = (int)sp_umulhi(g, inv_L);
+    const uint32_t pos = (((uint32_t)(j * L)) & 31u) + (g - (uint32_t)(j * L));
+    return rows[j * Ws + (pos >> 5)] >> (pos & 31u);
+}
+SPARC_HD void expand_base(const StoreDev& st, const uint32_t* rows, int32_t* out_tile, int nE, int tid, int nthr) {
+    const int L = st.L, Ws = st.W + 2, total = nE * L, nchunks = total >> 2;
     int c = tid;
     for (; c + 3 * nthr < nchunks; c += 4 * nthr) {             // 4 independent stores in flight per thread
         uint32_t n[4];
 #pragma unroll
-        for (int u = 0; u < 4; u++) { const int cc = c + u * nthr; n[u] = flat[cc >> 3] >> ((cc & 7) * 4); }
+        for (int u = 0; u < 4; u++) n[u] = row_fetch(rows, 4u * (uint32_t)(c + u * nthr), L, Ws, st.inv_L);
 #pragma unroll
         for (int u = 0; u < 4; u++)
             sp_st4(out_tile + 4 * (size_t)(c + u * nthr), n[u] & 1, (n[u] >> 1) & 1, (n[u] >> 2) & 1, (n[u] >> 3) & 1);
     }
     for (; c < nchunks; c += nthr) {
-        const uint32_t n = flat[c >> 3] >> ((c & 7) * 4);
+        const uint32_t n = row_fetch(rows, 4u * (uint32_t)c, L, Ws, st.inv_L);
         sp_st4(out_tile + 4 * (size_t)c, n & 1, (n >> 1) & 1, (n >> 2) & 1, (n >> 3) & 1);
     }
     for (int e = (nchunks << 2) + tid; e < total; e += nthr)    // tail (< 4 elements)
-        out_tile[e] = (flat[e >> 5] >> (e & 31)) & 1u;
+        out_tile[e] = row_fetch(rows, (uint32_t)e, L, Ws, st.inv_L) & 1u;
 }
-// colour plane: flat string of 4-bit colour ids -> int32 output (chunk c = 16 bits at 16c)
-SPARC_HD void expand_color(const uint32_t* cflat, int32_t* out_tile, int total, int tid, int nthr) {
-    const int nchunks = total >> 2;
+// colour plane: 4-bit colour ids -> int32 output (a chunk = 16 stream bits)
+SPARC_HD void expand_color(const StoreDev& st, const uint32_t* rows, int32_t* out_tile, int nE, int tid, int nthr) {
+    const int L = 4 * st.S, Ws = st.Wc + 2, total = nE * st.S, nchunks = total >> 2;
     for (int c = tid; c < nchunks; c += nthr) {
-        const uint32_t n = cflat[c >> 1] >> ((c & 1) * 16);
+        const uint32_t n = row_fetch(rows, 16u * (uint32_t)c, L, Ws, st.inv_4S);
         sp_st4(out_tile + 4 * (size_t)c, n & 15, (n >> 4) & 15, (n >> 8) & 15, (n >> 12) & 15);
     }
     for (int e = (nchunks << 2) + tid; e < total; e += nthr)
-        out_tile[e] = (cflat[e >> 3] >> ((e & 7) * 4)) & 15u;
+        out_tile[e] = row_fetch(rows, 4u * (uint32_t)e, L, Ws, st.inv_4S) & 15u;
 }
 // additional_info plane -> int64 output (two elements per 16-byte store).  The plane is almost
-// all zeros: the flat non-zero mask decides, and only marked nodes read their int32 value.
-SPARC_HD void expand_info(const StoreDev& st, const uint32_t* zflat, const uint32_t* tile_puzzle, int64_t* out_tile,
+// all zeros: the non-zero mask decides, and only marked nodes read their int32 value.
+SPARC_HD void expand_info(const StoreDev& st, const uint32_t* rows, const uint32_t* tile_puzzle, int64_t* out_tile,
                           int nE, int tid, int nthr) {
-    const int S = st.S, total = nE * S, nchunks = total >> 1;
+    const int S = st.S, Ws = st.nv + 2, total = nE * S, nchunks = total >> 1;
     for (int c = tid; c < nchunks; c += nthr) {
-        const uint32_t m = (zflat[c >> 4] >> ((c & 15) * 2)) & 3u;
+        const uint32_t e0 = 2u * (uint32_t)c;
+        const uint32_t m = row_fetch(rows, e0, S, Ws, st.inv_S) & 3u;
         int32_t a = 0, b = 0;
         if (m) {
-            const uint32_t e0 = 2u * (uint32_t)c;
             const int j = (int)sp_umulhi(e0, st.inv_S), r = (int)e0 - j * S;
             if (m & 1) a = sp_ldg(st.info + (size_t)tile_puzzle[j] * S + r);
             if (m & 2) {
@@ -748,30 +811,42 @@ SPARC_HD void expand_info(const StoreDev& st, const uint32_t* zflat, const uint3
     }
 }
 
-// shared-memory words a tile of `tile` envs needs: dyn | tile_puzzle | flat | cflat | zflat
-SPARC_HD int tile_smem_words(const StoreDev& st, int tile) {
-    return tile * (SPARC_DYN_STRIDE + 1) + ((tile * st.L + 31) >> 5) + ((tile * 4 * st.S + 31) >> 5) + ((tile * st.S + 31) >> 5) + 3;
+// shared-memory words: per-tile header (dyn rows + puzzle ids) and the three row sets
+SPARC_HD int tile_head_words(int tile) { return tile * (SPARC_DYN_STRIDE + 1); }
+SPARC_HD int tile_flat_words(const StoreDev& st, int tile) { return tile * ((st.W + 2) + (st.Wc + 2) + (st.nv + 2)); }
+// encoder for one tile: stage 1a, barrier, stage 1b, barrier, stage 2 (barriers among the nthr
+// encoding threads).  head = dyn[tile][9] | tile_puzzle[tile]; flats = base rows | colour rows | info rows
+SPARC_HD void encode_tile_stage1a(const StoreDev& st, const uint32_t* head, uint32_t* flats, int tile, int nE,
+                                  const SparcObsOut& obs, int tid, int nthr) {
+    const uint32_t* dyn = head;
+    const uint32_t* tile_puzzle = head + tile * SPARC_DYN_STRIDE;
+    uint32_t* rb = flats;
+    uint32_t* rc = rb + tile * (st.W + 2);
+    uint32_t* rz = rc + tile * (st.Wc + 2);
+    if (obs.base_dev) build_rows(PlaneSrc{st, dyn, tile_puzzle}, rb, nE, st.inv_wsb, tid, nthr);
+    if (obs.color_dev) build_rows(ColorSrc{st, tile_puzzle}, rc, nE, st.inv_wsc, tid, nthr);
+    if (obs.info_dev) build_rows(InfoNzSrc{st, tile_puzzle}, rz, nE, st.inv_wsz, tid, nthr);
 }
-// whole encoder for one tile; `sync` is __syncthreads on the device
-SPARC_HD void encode_tile_stage1(const StoreDev& st, uint32_t* smem, int tile, int nE, const SparcObsOut& obs, int tid, int nthr) {
-    uint32_t* dyn = smem;
-    uint32_t* tile_puzzle = dyn + tile * SPARC_DYN_STRIDE;
-    uint32_t* flat = tile_puzzle + tile;
-    uint32_t* cflat = flat + ((tile * st.L + 31) >> 5) + 1;
-    uint32_t* zflat = cflat + ((tile * 4 * st.S + 31) >> 5) + 1;
-    if (obs.base_dev) build_flat(PlaneSrc{st, dyn, tile_puzzle}, flat, nE, st.L, st.W, st.inv_L, tid, nthr);
-    if (obs.color_dev) build_flat(ColorSrc{st, tile_puzzle}, cflat, nE, 4 * st.S, st.Wc, st.inv_4S, tid, nthr);
-    if (obs.info_dev) build_flat(InfoNzSrc{st, tile_puzzle}, zflat, nE, st.S, st.nv, st.inv_S, tid, nthr);
+SPARC_HD void encode_tile_stage1b(const StoreDev& st, const uint32_t* head, uint32_t* flats, int tile, int nE,
+                                  const SparcObsOut& obs, int tid, int nthr) {
+    const uint32_t* dyn = head;
+    const uint32_t* tile_puzzle = head + tile * SPARC_DYN_STRIDE;
+    uint32_t* rb = flats;
+    uint32_t* rc = rb + tile * (st.W + 2);
+    uint32_t* rz = rc + tile * (st.Wc + 2);
+    if (obs.base_dev) build_tails(PlaneSrc{st, dyn, tile_puzzle}, rb, nE, 4, tid, nthr);
+    if (obs.color_dev) build_tails(ColorSrc{st, tile_puzzle}, rc, nE, 16, tid, nthr);
+    if (obs.info_dev) build_tails(InfoNzSrc{st, tile_puzzle}, rz, nE, 2, tid, nthr);
 }
-SPARC_HD void encode_tile_stage2(const StoreDev& st, const uint32_t* smem, int tile, int nE, long long env0,
-                                 const SparcObsOut& obs, int tid, int nthr) {
-    const uint32_t* tile_puzzle = smem + tile * SPARC_DYN_STRIDE;
-    const uint32_t* flat = tile_puzzle + tile;
-    const uint32_t* cflat = flat + ((tile * st.L + 31) >> 5) + 1;
-    const uint32_t* zflat = cflat + ((tile * 4 * st.S + 31) >> 5) + 1;
-    if (obs.base_dev) expand_flat(flat, obs.base_dev + (size_t)env0 * st.L, nE * st.L, tid, nthr);
-    if (obs.color_dev) expand_color(cflat, obs.color_dev + (size_t)env0 * st.S, nE * st.S, tid, nthr);
-    if (obs.info_dev) expand_info(st, zflat, tile_puzzle, obs.info_dev + (size_t)env0 * st.S, nE, tid, nthr);
+SPARC_HD void encode_tile_stage2(const StoreDev& st, const uint32_t* head, const uint32_t* flats, int tile, int nE,
+                                 long long env0, const SparcObsOut& obs, int tid, int nthr) {
+    const uint32_t* tile_puzzle = head + tile * SPARC_DYN_STRIDE;
+    const uint32_t* rb = flats;
+    const uint32_t* rc = rb + tile * (st.W + 2);
+    const uint32_t* rz = rc + tile * (st.Wc + 2);
+    if (obs.base_dev) expand_base(st, rb, obs.base_dev + (size_t)env0 * st.L, nE, tid, nthr);
+    if (obs.color_dev) expand_color(st, rc, obs.color_dev + (size_t)env0 * st.S, nE, tid, nthr);
+    if (obs.info_dev) expand_info(st, rz, tile_puzzle, obs.info_dev + (size_t)env0 * st.S, nE, tid, nthr);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -17,6 +17,9 @@ static StoreDev make_store(const SparcStoreDesc* d) {
     s.inv_S = (uint32_t)((1ull << 32) / (uint64_t)s.S) + 1u;
     s.inv_4S = (uint32_t)((1ull << 32) / (uint64_t)(4 * s.S)) + 1u;
     s.Wc = (4 * s.S + 31) / 32;
+    s.inv_wsb = (uint32_t)((1ull << 32) / (uint64_t)(s.W + 2)) + 1u;
+    s.inv_wsc = (uint32_t)((1ull << 32) / (uint64_t)(s.Wc + 2)) + 1u;
+    s.inv_wsz = (uint32_t)((1ull << 32) / (uint64_t)(s.nv + 2)) + 1u;
     s.hdr = d->headers; s.nb = d->node_boards; s.cb = d->cell_boards; s.sbits = d->static_bits;
     s.color4 = d->color4; s.info_nz = d->info_nz; s.info = d->info; s.shapes = d->shapes; s.trie = d->trie;
     return s;
@@ -40,7 +43,7 @@ int emu_launch(const SparcStoreDesc* desc, uint32_t* core, uint32_t* vis, int32_
     if (out) p.out = *out;
     if (obs) p.obs = *obs;
     const StoreDev& st = p.st;
-    std::vector<uint32_t> smem((size_t)tile_smem_words(st, tile) + 4, 0xDEADBEEFu);
+    std::vector<uint32_t> smem((size_t)tile_head_words(tile) + tile_flat_words(st, tile) + 4, 0xDEADBEEFu);
     std::vector<EnvRegs> regs(tile);
     for (long long env0 = 0; env0 < n_envs; env0 += tile) {
         const int nE = (int)((n_envs - env0) < tile ? (n_envs - env0) : tile);
@@ -53,8 +56,10 @@ int emu_launch(const SparcStoreDesc* desc, uint32_t* core, uint32_t* vis, int32_
             tile_puzzle[tid] = regs[tid].puzzle;
             write_dyn(st, dyn, tid, regs[tid]);
         }
-        for (int tid = 0; tid < nthr; tid++) encode_tile_stage1(st, dyn, tile, nE, p.obs, tid, nthr);
-        for (int tid = 0; tid < nthr; tid++) encode_tile_stage2(st, dyn, tile, nE, env0, p.obs, tid, nthr);
+        uint32_t* flats = dyn + tile_head_words(tile);
+        for (int tid = 0; tid < nthr; tid++) encode_tile_stage1a(st, dyn, flats, tile, nE, p.obs, tid, nthr);
+        for (int tid = 0; tid < nthr; tid++) encode_tile_stage1b(st, dyn, flats, tile, nE, p.obs, tid, nthr);
+        for (int tid = 0; tid < nthr; tid++) encode_tile_stage2(st, dyn, flats, tile, nE, env0, p.obs, tid, nthr);
     }
     return 0;
 }

@@ -41,7 +41,20 @@ def test_autoreset_next_step_cycles_puzzles():
     assert st[0] > 10 and st[4] > 0
 
 
-def test_gpu_matches_cpu_emulation_at_scale():
+@pytest.fixture(params=[("0", "8"), ("1", "32"), ("0", "32"), ("0", "128")], ids=lambda p: f"ring{p[0]}-tile{p[1]}")
+def kernel_variant(request, monkeypatch):
+    """Both kernels (one tile per CTA / persistent warp-specialised ring) and several CTA tilings."""
+    monkeypatch.setenv("SPARC_RING", request.param[0])
+    monkeypatch.setenv("SPARC_TILE", request.param[1])
+    return request.param
+
+
+def test_lockstep_under_every_kernel_variant(kernel_variant):
+    rows = gen_pool(6, [(2, 2), (4, 4), (6, 6)], RULES_FULL, seed0=90, extra_solutions=1)
+    run_lockstep(make_env, rows, 70, 40, True, 30, "next_step", "terminal", seed=2, follow=0.8)
+
+
+def test_gpu_matches_cpu_emulation_at_scale(kernel_variant):
     """65,536-env class sizes cannot be replayed by the Python oracle; compare the CUDA run with the
     same device code compiled for the CPU (itself pinned to the oracle by test_emu_parity.py)."""
     from emu.emu_env import EmuVecEnv

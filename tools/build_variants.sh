@@ -6,11 +6,9 @@ cd "$(dirname "$0")/.."
 SRC=sparc_gym_b200/csrc/sparc_b200.cu
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -shared -Xcompiler -fPIC"
 mkdir -p build/variants
-for mb in 1 4 6 8; do
-  for hint in cs wb; do
-    h=".$hint"; [ "$hint" = wb ] && h=""
-    nvcc $FLAGS -DSPARC_MINBLOCKS=$mb -DSPARC_STORE_HINT="\"$h\"" -o build/variants/lib_mb${mb}_${hint}.so $SRC &
-  done
+for pc in "8 8" "12 4" "10 6" "6 10" "12 8"; do
+  set -- $pc
+  nvcc $FLAGS -DRING_PROD=$1 -DRING_CONS=$2 -o build/variants/lib_ring_p$1_c$2.so $SRC &
 done
 wait
 ls -la build/variants
