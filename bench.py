@@ -45,6 +45,19 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(workload, n_env):
+    """dram__bytes_read.sum + dram__bytes_write.sum per k_env launch from the committed `ncu --set full` capture of
+    this workload (profiles/r1_traffic.json), or None when the capture does not match the run."""
+    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if not os.path.exists(p):
+        return None
+    with open(p) as f:
+        t = json.load(f).get(workload)
+    if not t or t.get("envs_per_launch") != n_env:
+        return None
+    return t["dram_bytes_per_launch"]
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons during the timed region."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -169,7 +182,7 @@ def main():
     import torch
     import torch.distributed as dist
     from sparc_gym_b200.dataset import config_pool
-    from sparc_gym_b200.vec_env import SparcVecEnv
+    from sparc_gym_b200.runner import ShardedRunner, reduce_stats
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
@@ -179,14 +192,17 @@ def main():
 
     t_build = time.perf_counter()
     rows = config_pool(cfg, n_puzzles=pool_n)
-    env = SparcVecEnv(rows, n_env, traceback=traceback, max_steps=max_steps, autoreset_mode=args.autoreset,
-                      puzzle_stride=1, validate=args.validate, device=dev, write_obs=not args.no_obs)
+    # env-sharded: rank r owns global envs [r*n_env, (r+1)*n_env); global env i starts on puzzle i mod pool
+    runner = ShardedRunner(rows, n_env * world, rank=rank, world=world, local_rank=local_rank, traceback=traceback,
+                           max_steps=max_steps, autoreset_mode=args.autoreset, puzzle_stride=1, validate=args.validate,
+                           write_obs=not args.no_obs)
+    env = runner.env
     st = env.store
     t_build = time.perf_counter() - t_build
     K, W = args.steps, args.warmup
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     actions = torch.randint(0, 4, (K + W, n_env), dtype=torch.uint8, device=dev, generator=gen)
-    env.reset()
+    runner.reset()
     for t in range(W):
         env.step(actions[t])
     torch.cuda.synchronize()
@@ -258,13 +274,9 @@ def main():
                       "truncated u8 out; observation tensors stay on the device for the policy)"}
 
     # ---- episode statistics: the only cross-GPU traffic (NCCL all-reduce of int64[8])
-    stats = env.stats().clone()
-    if world > 1:
-        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
-    stats = stats.cpu().tolist()
+    stats = reduce_stats(env.stats())
 
     if rank == 0:
-        from sparc_gym_b200 import abi
         peak, peak_src = measured_peaks()
         b_alg = st.algorithmic_bytes_per_step()
         value = n_env * world * K / (ms_max / 1e3)
@@ -286,10 +298,10 @@ def main():
                        "parallelism": f"env-sharded x{world}, no data-path collective", "setup_s": round(t_build, 1)},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                         "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                         "frac": round(achieved / peak, 4), "traffic": ncu_traffic(args.workload, n_env), "peak_source": peak_src,
                          "kernel": "k_env", "algorithmic_bytes_per_env_step": b_alg,
                          "envs_per_launch": n_env, "kernel_ms": round(kernel_ms, 5)},
-            "episode_stats": dict(zip(abi.STAT_NAMES, stats)),
+            "episode_stats": stats,
         }
         if not args.no_cpu_baseline and world == 1:
             # fresh interpreter: the worker pool must not be forked from a process holding a CUDA context

@@ -1,0 +1,48 @@
+"""GPU: the single-env Gymnasium drop-in reproduces the golden traces recorded from the UNMODIFIED
+reference (tests/golden/traces.json.gz) -- dict key order, shapes, dtypes, reward value AND Python
+type, legal actions, rule flags, region summaries -- step by step."""
+import gzip
+import json
+import os
+
+import pytest
+
+from tracing import diff_traces, run_episode
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_dropin_replays_reference_traces():
+    import sparc_gym_b200
+    with gzip.open(os.path.join(G, "traces.json.gz"), "rb") as f:
+        g = json.loads(f.read())
+    envs, steps = {}, 0
+    for ep in g["episodes"]:
+        key = (ep["traceback"], ep["max_steps"])
+        if key not in envs:
+            envs[key] = sparc_gym_b200.make("SPaRc-Gym", puzzles=g["rows"], observation="new",
+                                            traceback=key[0], max_steps=key[1])
+        row = g["rows"][ep["row"]]
+        got = run_episode(envs[key], row["id"], ep["actions"])
+        d = diff_traces(ep["trace"], json.loads(json.dumps(got)))
+        assert d is None, f"{row['id']} traceback={key[0]}: {d}"
+        steps += len(got)
+    assert steps > 3000
+
+
+def test_reset_cursor_matches_reference():
+    import sparc_gym_b200
+    with gzip.open(os.path.join(G, "resets.json.gz"), "rb") as f:
+        g = json.loads(f.read())
+    env = sparc_gym_b200.SPaRC_Gym(puzzles=g["rows"], max_steps=10)
+    for s, want in zip(g["script"], g["index"]):
+        if s[0] == "none":
+            env.reset()
+        elif s[0] == "seed":
+            env.reset(seed=s[1])
+        elif s[0] == "id":
+            env.reset(options={"puzzle_id": s[1]})
+        else:
+            env.reset(seed=s[1], options={"puzzle_id": s[2]})
+        assert env.current_puzzle_index == want, s
