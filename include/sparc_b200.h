@@ -193,6 +193,10 @@ int sparc_reset(SparcEnv* env, const int32_t* puzzle_idx_dev, const uint8_t* mas
 int sparc_step(SparcEnv* env, const void* actions_dev, int action_dtype,
                const SparcStepOut* out, const SparcObsOut* obs, void* stream);
 
+/* replaces _get_obs() (SG.py:956-979) on its own: rewrite the observation of every env from the
+ * current state without stepping (after sparc_state_load, or to fill a second buffer). */
+int sparc_encode(SparcEnv* env, const SparcObsOut* obs, void* stream);
+
 /* replaces _validate_rules() (SG.py:941-950) on the current state of the masked envs (NULL = all).
  * flags_dev: uint16[n_envs]; region_map_dev: int8[n_envs][slab_x][slab_y] (-1 off-cell,
  * SG.py:429-454) or NULL. */

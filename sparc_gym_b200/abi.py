@@ -30,7 +30,7 @@ ACT_DTYPES = {"uint8": 0, "int32": 1, "int64": 2}
 REWARD_VALUES = (0, 0.01, -0.01, 1, -1)      # reward code -> the reference's Python value (SG.py:1204-1223)
 
 EXPORTS = ("sparc_abi_version", "sparc_last_error", "sparc_store_create", "sparc_store_destroy",
-           "sparc_env_create", "sparc_env_destroy", "sparc_reset", "sparc_step", "sparc_validate",
+           "sparc_env_create", "sparc_env_destroy", "sparc_reset", "sparc_step", "sparc_encode", "sparc_validate",
            "sparc_stats", "sparc_step_host", "sparc_state_bytes", "sparc_state_save",
            "sparc_state_load", "sparc_env_num_envs", "sparc_kernel_launches")
 
@@ -99,6 +99,7 @@ def load_library():
     lib.sparc_env_destroy.argtypes = [vp]
     lib.sparc_reset.argtypes = [vp, vp, vp, C.POINTER(StepOut), C.POINTER(ObsOut), vp]
     lib.sparc_step.argtypes = [vp, vp, i32, C.POINTER(StepOut), C.POINTER(ObsOut), vp]
+    lib.sparc_encode.argtypes = [vp, C.POINTER(ObsOut), vp]
     lib.sparc_validate.argtypes = [vp, vp, vp, vp, vp]
     lib.sparc_stats.argtypes = [vp, vp, i32, vp]
     lib.sparc_step_host.argtypes = [vp, vp, vp, vp, vp, C.POINTER(ObsOut), vp]

@@ -41,6 +41,13 @@ struct SparcEnv {
     StepCfg cfg;
     StateDev s;
     int tile;                // envs per CTA
+    int split_chunks;        // >0: k_dyn / k_encode pipeline over this many env chunks
+    int enc_tile;            // envs per k_encode CTA
+    cudaStream_t side;       // high-priority stream of k_dyn (multi-chunk) / k_val
+    cudaEvent_t ev_start, ev_dyn[16], ev_val;
+    uint32_t* vq_count;      // deferred-validation queue (split path, validate = terminal)
+    uint32_t* vq;
+    int val_grid;
     int ring_grid;           // >0: use k_env_ring with this many persistent CTAs (one per SM)
     unsigned int* sched;     // [2] tile counter + finished-producer counter of k_env_ring
     int64_t launches;
@@ -89,6 +96,72 @@ __global__ void __launch_bounds__(CTA_THREADS, SPARC_MINBLOCKS) k_env(const KPar
     encode_tile_stage1b(st, head, flats, p.tile, nE, p.obs, tid, CTA_THREADS);
     __syncthreads();
     encode_tile_stage2(st, head, flats, p.tile, nE, env0, p.obs, tid, CTA_THREADS);
+}
+
+// ---- split pair for big batches: k_dyn (latency bound) || k_encode (bandwidth bound) -------------
+// The observation is a pure function of the env state, so the step splits into a dynamics kernel
+// (one env per thread, every lane busy) and an encoder kernel that streams state -> observation.
+// sparc_step cuts the batch into chunks and runs k_dyn(chunk c+1) on a high-priority side stream
+// while k_encode(chunk c) streams on the caller's stream: the dependent-load chains of the
+// dynamics overlap the HBM-bound stores instead of sitting in front of them.
+#ifndef DYN_MINBLOCKS
+#define DYN_MINBLOCKS 1
+#endif
+// INLINE_VALIDATION = false: terminal states are only queued (k_val validates them), which drops the
+// validator from this kernel's register budget (145 -> ~60) and doubles its resident warps.
+template <bool INLINE_VALIDATION>
+__global__ void __launch_bounds__(CTA_THREADS, DYN_MINBLOCKS) k_dyn(const KParams p, long long lo, long long hi) {
+    const long long i = lo + (long long)blockIdx.x * CTA_THREADS + threadIdx.x;
+    EnvRegs e;
+    unsigned long long my_stats[SPARC_N_STATS];
+    uint32_t scratch[SPARC_DYN_STRIDE];
+    bool have_stats = false;
+    if (i < hi) have_stats = phase_a<INLINE_VALIDATION>(p, i, e, scratch, my_stats);
+    if (p.mode == 0) reduce_stats(p, have_stats, my_stats);
+}
+
+// deferred terminal validation: a small persistent grid walks the queue k_dyn filled
+__global__ void __launch_bounds__(CTA_THREADS) k_val(const KParams p) {
+    const uint32_t count = *p.vq_count;
+    unsigned long long pass = 0;
+    for (uint32_t slot = blockIdx.x * CTA_THREADS + threadIdx.x; slot < count; slot += gridDim.x * CTA_THREADS)
+        pass += (unsigned long long)validate_queued(p, slot);
+#pragma unroll
+    for (int off = 16; off; off >>= 1) pass += __shfl_down_sync(0xffffffffu, pass, off);
+    if ((threadIdx.x & 31) == 0 && pass) atomicAdd(p.sd.stats + SPARC_STAT_RULES_PASS, pass);
+    __syncthreads();                                             // every thread of the CTA has read `count`
+    if (threadIdx.x == 0) {                                      // last CTA out empties the queue for the next step
+        __threadfence();
+        if (atomicAdd(p.vq_count + 1, 1u) == gridDim.x - 1) { p.vq_count[0] = 0; p.vq_count[1] = 0; }
+    }
+}
+
+#ifndef ENC_THREADS
+#define ENC_THREADS 128
+#endif
+#ifndef ENC_MINBLOCKS
+#define ENC_MINBLOCKS 8
+#endif
+__global__ void __launch_bounds__(ENC_THREADS, ENC_MINBLOCKS) k_encode(const KParams p, long long lo, long long hi) {
+    const StoreDev& st = p.st;
+    const int tid = threadIdx.x;
+    const long long env0 = lo + (long long)blockIdx.x * p.tile;
+    const int nE = (int)min((long long)p.tile, hi - env0);
+    uint32_t* head = smem;
+    uint32_t* flats = smem + tile_head_words(p.tile);
+    if (tid < nE) {
+        EnvRegs e;
+        load_env(e, p.sd, st, p.cfg.n_envs, env0 + tid);
+        prefetch_static(st, e.puzzle);
+        head[p.tile * SPARC_DYN_STRIDE + tid] = e.puzzle;
+        write_dyn(st, head, tid, e);
+    }
+    __syncthreads();
+    encode_tile_stage1a(st, head, flats, p.tile, nE, p.obs, tid, ENC_THREADS);
+    __syncthreads();
+    encode_tile_stage1b(st, head, flats, p.tile, nE, p.obs, tid, ENC_THREADS);
+    __syncthreads();
+    encode_tile_stage2(st, head, flats, p.tile, nE, env0, p.obs, tid, ENC_THREADS);
 }
 
 // ---- ring kernel: one persistent, warp-specialised CTA per SM -------------------------------------
@@ -439,10 +512,38 @@ int sparc_env_create(SparcStore* store, int64_t n_envs, int traceback, int max_s
         const size_t shmem = (size_t)(tile_head_words(e->tile) + tile_flat_words(store->d, e->tile)) * sizeof(uint32_t);
         if (shmem > 48 * 1024) {
             cudaError_t ae = cudaFuncSetAttribute(k_env, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem);
+            if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem);
             if (ae != cudaSuccess) { delete e; return fail(SPARC_E_CUDA, "k_env shared memory: %s", cudaGetErrorString(ae)); }
         }
     }
-    {   // big batches: the ring kernel, one persistent CTA per SM
+    {   // big batches: the k_dyn || k_encode pipeline
+        const char* pe = getenv("SPARC_SPLIT");                // chunks; 0 = fused k_env; unset = automatic
+        int nc = pe ? atoi(pe) : (n_envs >= 32768 ? 1 : 0);   // measured: 1 chunk (k_dyn then k_encode) is fastest
+        if (nc > 16) nc = 16;
+        const char* te = getenv("SPARC_ENC_TILE");
+        e->enc_tile = te ? atoi(te) : 8;
+        if (e->enc_tile < 4 || e->enc_tile > ENC_THREADS || e->enc_tile % 4) e->enc_tile = 8;
+        if (nc > 0) {
+            int lo_p = 0, hi_p = 0;
+            cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p);
+            cudaError_t se = cudaStreamCreateWithPriority(&e->side, cudaStreamNonBlocking, hi_p);
+            if (se == cudaSuccess) se = cudaEventCreateWithFlags(&e->ev_start, cudaEventDisableTiming);
+            for (int c = 0; c < nc && se == cudaSuccess; c++) se = cudaEventCreateWithFlags(&e->ev_dyn[c], cudaEventDisableTiming);
+            if (se == cudaSuccess) se = cudaEventCreateWithFlags(&e->ev_val, cudaEventDisableTiming);
+            const char* de = getenv("SPARC_DEFER_VALIDATION");
+            if (se == cudaSuccess && !(de && atoi(de) == 0)) {
+                se = cudaMalloc((void**)&e->vq_count, 2 * sizeof(uint32_t));   // count, finished k_val CTAs
+                if (se == cudaSuccess) se = cudaMalloc((void**)&e->vq, (size_t)n_envs * SPARC_VQ_WORDS * sizeof(uint32_t));
+                if (se == cudaSuccess) se = cudaMemset(e->vq_count, 0, 2 * sizeof(uint32_t));
+                int dev_sms = 0;
+                cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, store->device);
+                e->val_grid = dev_sms > 0 ? dev_sms : 148;
+            }
+            if (se != cudaSuccess) { delete e; return fail(SPARC_E_CUDA, "side stream / queue: %s", cudaGetErrorString(se)); }
+            e->split_chunks = nc;
+        }
+    }
+    {   // opt-in: the ring kernel, one persistent CTA per SM
         int dev_sms = 0;
         cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, store->device);
         const char* pe = getenv("SPARC_RING");
@@ -480,8 +581,12 @@ int sparc_env_create(SparcStore* store, int64_t n_envs, int traceback, int max_s
 int sparc_env_destroy(SparcEnv* e) {
     if (!e) return SPARC_OK;
     cudaSetDevice(e->store->device);
-    void* ptrs[] = {e->s.core, e->s.vis, e->s.ep_ret, e->s.moves, e->s.stats, e->sched, e->act_stage, e->rew_stage, e->term_stage, e->trunc_stage};
+    void* ptrs[] = {e->s.core, e->s.vis, e->s.ep_ret, e->s.moves, e->s.stats, e->sched, e->vq_count, e->vq, e->act_stage, e->rew_stage, e->term_stage, e->trunc_stage};
     for (void* p : ptrs) if (p) cudaFree(p);
+    if (e->side) cudaStreamDestroy(e->side);
+    if (e->ev_start) cudaEventDestroy(e->ev_start);
+    for (cudaEvent_t ev : e->ev_dyn) if (ev) cudaEventDestroy(ev);
+    if (e->ev_val) cudaEventDestroy(e->ev_val);
     delete e;
     return SPARC_OK;
 }
@@ -490,6 +595,47 @@ static int launch_env(SparcEnv* e, KParams& p, void* stream) {
     p.st = e->store->d; p.sd = e->s; p.cfg = e->cfg; p.tile = e->tile;
     const int64_t n = e->cfg.n_envs;
     const unsigned ntiles = (unsigned)((n + e->tile - 1) / e->tile);
+    if (e->split_chunks > 0) {
+        // chunk c: [k_dyn on the side stream] -> event -> [k_encode on the caller's stream]
+        cudaStream_t s0 = (cudaStream_t)stream;
+        const bool any_obs = p.obs.base_dev || p.obs.color_dev || p.obs.info_dev;
+        const int nc = e->split_chunks;
+        const int64_t per = ((n + nc - 1) / nc + 127) / 128 * 128;       // chunk boundaries stay 16-B aligned in every stream
+        p.tile = e->enc_tile;
+        const size_t shmem = (size_t)(tile_head_words(p.tile) + tile_flat_words(p.st, p.tile)) * sizeof(uint32_t);
+        cudaStream_t sd = nc > 1 ? e->side : s0;                         // one chunk: plain back-to-back launches
+        const bool defer = nc == 1 && p.mode == 0 && e->vq && e->cfg.validate_mode == SPARC_VALIDATE_TERMINAL;
+        if (defer) {
+            p.vq = e->vq; p.vq_count = e->vq_count;                     // (k_val leaves the queue empty)
+        }
+        if (nc > 1) {
+            CU(cudaEventRecord(e->ev_start, s0));
+            CU(cudaStreamWaitEvent(e->side, e->ev_start, 0));
+        }
+        for (int c = 0; c < nc; c++) {
+            const long long lo = (long long)c * per, hi = lo + per < n ? lo + per : n;
+            if (lo >= hi) break;
+            const unsigned dgrid = (unsigned)((hi - lo + CTA_THREADS - 1) / CTA_THREADS);
+            if (defer) k_dyn<false><<<dgrid, CTA_THREADS, 0, sd>>>(p, lo, hi);
+            else k_dyn<true><<<dgrid, CTA_THREADS, 0, sd>>>(p, lo, hi);
+            if (nc > 1) {
+                CU(cudaEventRecord(e->ev_dyn[c], e->side));
+                CU(cudaStreamWaitEvent(s0, e->ev_dyn[c], 0));
+            }
+            if (defer) {                                                     // fork: k_val beside k_encode
+                CU(cudaEventRecord(e->ev_start, s0));
+                CU(cudaStreamWaitEvent(e->side, e->ev_start, 0));
+                k_val<<<(unsigned)e->val_grid, CTA_THREADS, 0, e->side>>>(p);
+                CU(cudaEventRecord(e->ev_val, e->side));
+                e->launches++;
+            }
+            if (any_obs) k_encode<<<(unsigned)((hi - lo + p.tile - 1) / p.tile), ENC_THREADS, shmem, s0>>>(p, lo, hi);
+            if (defer) CU(cudaStreamWaitEvent(s0, e->ev_val, 0));            // join
+            e->launches += any_obs ? 2 : 1;
+        }
+        CU(cudaGetLastError());
+        return SPARC_OK;
+    }
     if (e->ring_grid > 0) {
         p.tile = RING_TILE;
         const size_t shmem = (size_t)(4 * RING_PROD + RING_PROD * ring_slot_words(p.st) + RING_CONS * 2 * STAGE_WORDS) * sizeof(uint32_t);
@@ -521,6 +667,19 @@ int sparc_step(SparcEnv* e, const void* actions_dev, int action_dtype, const Spa
     if (out) p.out = *out;
     if (obs) p.obs = *obs;
     return launch_env(e, p, stream);
+}
+
+int sparc_encode(SparcEnv* e, const SparcObsOut* obs, void* stream) {
+    if (!e || !obs) return fail(SPARC_E_ARG, "null argument%s");
+    KParams p; memset(&p, 0, sizeof(p));
+    p.st = e->store->d; p.sd = e->s; p.cfg = e->cfg; p.obs = *obs;
+    const int64_t n = e->cfg.n_envs;
+    p.tile = e->split_chunks > 0 ? e->enc_tile : (e->tile <= ENC_THREADS ? e->tile : 32);
+    const size_t shmem = (size_t)(tile_head_words(p.tile) + tile_flat_words(p.st, p.tile)) * sizeof(uint32_t);
+    k_encode<<<(unsigned)((n + p.tile - 1) / p.tile), ENC_THREADS, shmem, (cudaStream_t)stream>>>(p, 0, n);
+    CU(cudaGetLastError());
+    e->launches++;
+    return SPARC_OK;
 }
 
 int sparc_validate(SparcEnv* e, const uint8_t* mask_dev, uint16_t* flags_dev, int8_t* region_map_dev, void* stream) {

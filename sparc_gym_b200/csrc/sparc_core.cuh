@@ -864,7 +864,10 @@ struct KParams {
     const uint8_t* reset_mask;
     SparcStepOut out;
     SparcObsOut obs;
+    uint32_t* vq_count;      // deferred terminal validation: number of queued envs (nullptr = validate inline)
+    uint32_t* vq;            // [n_envs][SPARC_VQ_WORDS]: env, puzzle, x | y << 8, pad, visited[8]
 };
+#define SPARC_VQ_WORDS 12
 
 SPARC_HD long long load_action(const void* p, int dtype, long long i) {
     if (dtype == SPARC_ACT_U8) return reinterpret_cast<const uint8_t*>(p)[i];
@@ -880,6 +883,7 @@ SPARC_HD float reward_value(int code) {
 // Phase A for env i (one thread): reset / autoreset / frozen / live step, terminal validation,
 // per-env outputs.  `scratch` = 9 words the validator may use.  Returns true when `stats`
 // (SPARC_N_STATS counters) were filled.  On exit `e` is the state the observation must show.
+template <bool INLINE_VALIDATION = true>
 SPARC_HD bool phase_a(const KParams& p, long long i, EnvRegs& e, uint32_t* scratch, unsigned long long* stats) {
     const StoreDev& st = p.st;
     const long long n = p.cfg.n_envs;
@@ -911,10 +915,25 @@ SPARC_HD bool phase_a(const KParams& p, long long i, EnvRegs& e, uint32_t* scrat
         const bool done = r.terminated || r.truncated;
         if (p.cfg.validate_mode == SPARC_VALIDATE_EVERY_STEP ||
             (p.cfg.validate_mode == SPARC_VALIDATE_TERMINAL && done)) {
+            if (!INLINE_VALIDATION || (p.vq_count && p.cfg.validate_mode == SPARC_VALIDATE_TERMINAL)) {
+                // Terminal states are rare (1-2 % of the envs per step) and validating one inline idles
+                // the 31 other lanes of its warp for the whole flood fill: queue a snapshot instead;
+                // validate_queued() runs densely packed, beside the observation encoder.
+#if defined(__CUDA_ARCH__)
+                const uint32_t slot = atomicAdd(p.vq_count, 1u);
+#else
+                const uint32_t slot = (*p.vq_count)++;
+#endif
+                uint32_t* q = p.vq + (size_t)slot * SPARC_VQ_WORDS;
+                q[0] = (uint32_t)i; q[1] = e.puzzle; q[2] = (uint32_t)e.x | ((uint32_t)e.y << 8); q[3] = 0;
 #pragma unroll
-            for (int k = 0; k < 8; k++) scratch[k] = e.v[k];
-            scratch[8] = 0;
-            r.rule_flags = validate_env(st, e.puzzle, scratch, e.x, e.y, nullptr) | SPARC_RULE_VALID;
+                for (int k = 0; k < 8; k++) q[4 + k] = e.v[k];
+            } else if (INLINE_VALIDATION) {
+#pragma unroll
+                for (int k = 0; k < 8; k++) scratch[k] = e.v[k];
+                scratch[8] = 0;
+                r.rule_flags = validate_env(st, e.puzzle, scratch, e.x, e.y, nullptr) | SPARC_RULE_VALID;
+            }
         }
 #pragma unroll
         for (int k = 0; k < SPARC_N_STATS; k++) stats[k] = 0;
@@ -948,4 +967,17 @@ SPARC_HD bool phase_a(const KParams& p, long long i, EnvRegs& e, uint32_t* scrat
     if (p.out.step_count_dev) p.out.step_count_dev[i] = (int32_t)e.step;
     if (p.out.agent_xy_dev) { p.out.agent_xy_dev[2 * i] = (uint8_t)e.x; p.out.agent_xy_dev[2 * i + 1] = (uint8_t)e.y; }
     return have_stats;
+}
+
+// deferred terminal validation of queue entry `slot`: writes the env's rule flags, returns 1 when
+// all rules are satisfied (for the RULES_PASS statistic)
+SPARC_HD int validate_queued(const KParams& p, uint32_t slot) {
+    const uint32_t* q = p.vq + (size_t)slot * SPARC_VQ_WORDS;
+    uint32_t vd[SPARC_DYN_STRIDE];
+#pragma unroll
+    for (int k = 0; k < 8; k++) vd[k] = q[4 + k];
+    vd[8] = 0;
+    const int f = validate_env(p.st, q[1], vd, (int)(q[2] & 0xff), (int)((q[2] >> 8) & 0xff), nullptr) | SPARC_RULE_VALID;
+    if (p.out.rule_flags_dev) p.out.rule_flags_dev[q[0]] = (uint16_t)f;
+    return (f & SPARC_RULE_ALL) != 0;
 }

@@ -156,6 +156,12 @@ class SparcVecEnv:
                                                ptr(truncated_host),
                                                C.byref(self._obs_out if self.write_obs else self._no_obs), self._stream()))
 
+    def encode(self):
+        """Rewrite the observation tensors from the current state without stepping (sparc_encode)."""
+        with torch.cuda.device(self.device):
+            abi.check(self.lib.sparc_encode(self.handle, C.byref(self._obs_out), self._stream()))
+        return self.obs
+
     def validate(self, mask=None, region_map=False):
         """Rule validation of the current state (SG.py:941-950): uint16 flags (as int16 bit
         patterns) and optionally the region map int8[N, X, Y] (-1 off-cell, SG.py:429-454)."""

@@ -31,7 +31,8 @@ extern "C" {
 int emu_launch(const SparcStoreDesc* desc, uint32_t* core, uint32_t* vis, int32_t* ep_ret, uint32_t* moves,
                unsigned long long* stats, long long n_envs, int traceback, int max_steps, int autoreset,
                int stride, int validate_mode, int mode, int tile, int nthr, const void* actions, int act_dtype,
-               const int32_t* reset_idx, const uint8_t* reset_mask, const SparcStepOut* out, const SparcObsOut* obs) {
+               const int32_t* reset_idx, const uint8_t* reset_mask, const SparcStepOut* out, const SparcObsOut* obs,
+               int defer_validation) {
     KParams p;
     memset(&p, 0, sizeof(p));
     p.st = make_store(desc);
@@ -42,6 +43,9 @@ int emu_launch(const SparcStoreDesc* desc, uint32_t* core, uint32_t* vis, int32_
     p.reset_idx = reset_idx; p.reset_mask = reset_mask;
     if (out) p.out = *out;
     if (obs) p.obs = *obs;
+    std::vector<uint32_t> vq;
+    uint32_t vq_count = 0;
+    if (defer_validation) { vq.resize((size_t)n_envs * SPARC_VQ_WORDS); p.vq = vq.data(); p.vq_count = &vq_count; }
     const StoreDev& st = p.st;
     std::vector<uint32_t> smem((size_t)tile_head_words(tile) + tile_flat_words(st, tile) + 4, 0xDEADBEEFu);
     std::vector<EnvRegs> regs(tile);
@@ -61,6 +65,7 @@ int emu_launch(const SparcStoreDesc* desc, uint32_t* core, uint32_t* vis, int32_
         for (int tid = 0; tid < nthr; tid++) encode_tile_stage1b(st, dyn, flats, tile, nE, p.obs, tid, nthr);
         for (int tid = 0; tid < nthr; tid++) encode_tile_stage2(st, dyn, flats, tile, nE, env0, p.obs, tid, nthr);
     }
+    for (uint32_t slot = 0; slot < vq_count; slot++) stats[SPARC_STAT_RULES_PASS] += validate_queued(p, slot);
     return 0;
 }
 

@@ -28,7 +28,7 @@ def build_emu():
 
 class EmuVecEnv:
     def __init__(self, puzzles, num_envs, traceback=False, max_steps=2000, autoreset_mode="next_step",
-                 puzzle_stride=1, validate="terminal", slab=None, planes="auto", tile=8, nthr=128):
+                 puzzle_stride=1, validate="terminal", slab=None, planes="auto", tile=8, nthr=128, defer_validation=False):
         if not isinstance(puzzles, PuzzleStore):
             if puzzles and isinstance(puzzles[0], dict):
                 puzzles = ingest_rows(puzzles)
@@ -39,7 +39,7 @@ class EmuVecEnv:
         N = self.num_envs = int(num_envs)
         self.cfg = (int(bool(traceback)), int(max_steps), abi.AUTORESET[autoreset_mode], int(puzzle_stride),
                     abi.VALIDATE[validate])
-        self.tile, self.nthr = tile, nthr
+        self.tile, self.nthr, self.defer = tile, nthr, int(defer_validation)
         self.core = np.zeros((N, 4), np.uint32)
         self.core[:, 0] = np.arange(N) % st.n_puzzles
         self.vis = np.zeros((8, N), np.uint32)
@@ -66,7 +66,7 @@ class EmuVecEnv:
         p = lambda a: C.c_void_p(a.ctypes.data) if a is not None else None
         rc = self.lib.emu_launch(C.byref(self.desc), p(self.core), p(self.vis), p(self.ep_ret), p(self.moves),
                                  p(self.stats_acc), C.c_longlong(self.num_envs), *self.cfg, mode, self.tile, self.nthr,
-                                 p(actions), dtype, p(idx), p(mask), C.byref(self._step_out), C.byref(self._obs_out))
+                                 p(actions), dtype, p(idx), p(mask), C.byref(self._step_out), C.byref(self._obs_out), self.defer)
         assert rc == 0
 
     def _info(self):

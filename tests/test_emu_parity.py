@@ -50,9 +50,28 @@ def test_fuzz_rows_every_step_validation(traceback):
     run_lockstep(EmuVecEnv, rows, 36, 45, traceback, 40, "disabled", "every_step", seed=3)
 
 
-def test_full_rules_mixed_sizes_terminal_validation():
+@pytest.mark.parametrize("defer", [False, True])
+def test_full_rules_mixed_sizes_terminal_validation(defer):
     rows = gen_pool(8, [(3, 3), (4, 4), (5, 5), (6, 6)], RULES_FULL, seed0=40, extra_solutions=1)
-    run_lockstep(EmuVecEnv, rows, 24, 90, True, 80, "disabled", "terminal", seed=5, follow=0.97)
+    make = lambda *a, **k: EmuVecEnv(*a, defer_validation=defer, **k)
+    env, _ = run_lockstep(make, rows, 24, 90, True, 80, "disabled", "terminal", seed=5, follow=0.97)
+    assert env.stats()[7] > 0                     # some episodes ended with every rule satisfied
+
+
+def test_deferred_validation_with_same_step_autoreset():
+    """The queue snapshot must hold the TERMINAL state although the env is reset in the same step."""
+    rows = gen_pool(6, [(2, 2), (3, 3), (4, 4)], RULES_FULL, seed0=21)
+    a = EmuVecEnv(rows, 40, traceback=False, max_steps=30, autoreset_mode="same_step", validate="terminal")
+    b = EmuVecEnv(rows, 40, traceback=False, max_steps=30, autoreset_mode="same_step", validate="terminal",
+                  defer_validation=True, tile=32)
+    a.reset(); b.reset()
+    rng = np.random.default_rng(3)
+    for t in range(80):
+        act = rng.integers(0, 4, 40).astype(np.uint8)
+        ra, rb = a.step(act), b.step(act)
+        assert np.array_equal(ra[4]["rule_flags"], rb[4]["rule_flags"]), t
+        assert np.array_equal(ra[0]["base"], rb[0]["base"]) and np.array_equal(ra[1], rb[1])
+    assert np.array_equal(a.stats(), b.stats()) and a.stats()[0] > 50
 
 
 def test_autoreset_next_step_cycles_puzzles():

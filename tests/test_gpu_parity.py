@@ -41,11 +41,15 @@ def test_autoreset_next_step_cycles_puzzles():
     assert st[0] > 10 and st[4] > 0
 
 
-@pytest.fixture(params=[("0", "8"), ("1", "32"), ("0", "32"), ("0", "128")], ids=lambda p: f"ring{p[0]}-tile{p[1]}")
+@pytest.fixture(params=[("0", "0", "8"), ("0", "1", "32"), ("0", "0", "128"), ("3", "0", "8"), ("4", "0", "32"), ("1", "0", "4")],
+                ids=lambda p: f"split{p[0]}-ring{p[1]}-tile{p[2]}")
 def kernel_variant(request, monkeypatch):
-    """Both kernels (one tile per CTA / persistent warp-specialised ring) and several CTA tilings."""
-    monkeypatch.setenv("SPARC_RING", request.param[0])
-    monkeypatch.setenv("SPARC_TILE", request.param[1])
+    """Every launch strategy: fused k_env at several CTA tilings, the persistent warp-specialised ring
+    kernel, and the k_dyn || k_encode chunk pipeline (side stream + events)."""
+    monkeypatch.setenv("SPARC_SPLIT", request.param[0])
+    monkeypatch.setenv("SPARC_RING", request.param[1])
+    monkeypatch.setenv("SPARC_TILE", request.param[2])
+    monkeypatch.setenv("SPARC_ENC_TILE", request.param[2])
     return request.param
 
 
@@ -77,3 +81,27 @@ def test_gpu_matches_cpu_emulation_at_scale(kernel_variant):
         assert np.array_equal(to_np(gi["rule_flags"]).astype(np.uint16), ci["rule_flags"]), t
     assert np.array_equal(to_np(g.stats()), c.stats())
     assert c.stats()[0] > 1000
+
+
+def test_checkpoint_restore_and_standalone_encode():
+    """state_dict -> steps -> load_state_dict -> encode() gives back the checkpointed observation, and
+    the restored env continues exactly like a twin that never left (sparc_state_save/load, sparc_encode)."""
+    rows = gen_pool(6, [(3, 3), (5, 5)], RULES_FULL, seed0=77)
+    a, b = make_env(rows, 300, traceback=True, max_steps=25), make_env(rows, 300, traceback=True, max_steps=25)
+    a.reset(); b.reset()
+    rng = np.random.default_rng(8)
+    acts = [torch.from_numpy(rng.integers(0, 4, 300).astype(np.uint8)).cuda() for _ in range(30)]
+    for t in range(10):
+        a.step(acts[t]); b.step(acts[t])
+    ck = a.state_dict()
+    want = {k: v.clone() for k, v in a.obs.items()}
+    for t in range(10, 20):
+        a.step(acts[t])
+    a.load_state_dict(ck)
+    got = a.encode()
+    for k in want:
+        assert torch.equal(got[k], want[k]), k
+    for t in range(10, 30):
+        ra, rb = a.step(acts[t]), b.step(acts[t])
+        assert torch.equal(ra[1], rb[1]) and torch.equal(ra[2], rb[2]) and torch.equal(ra[3], rb[3])
+        assert all(torch.equal(ra[0][k], rb[0][k]) for k in ra[0])
