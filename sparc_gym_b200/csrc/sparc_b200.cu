@@ -120,7 +120,11 @@ __global__ void __launch_bounds__(CTA_THREADS, DYN_MINBLOCKS) k_dyn(const KParam
     if (p.mode == 0) reduce_stats(p, have_stats, my_stats);
 }
 
-// deferred terminal validation: a small persistent grid walks the queue k_dyn filled
+// deferred terminal validation: a small grid walks the queue k_dyn filled, one snapshot per thread.
+// (A warp-per-snapshot variant -- every lane floods from a different rule cell, the first cell of
+// each region checks its rules -- was measured: it bounds the many-region tail but doubles the
+// mean, because typical terminal states have 1-3 regions and 36 cells need two flood rounds:
+// k_val 47 -> 95 us, step 0.205 -> 0.230 ms.  Kept serial.)
 __global__ void __launch_bounds__(CTA_THREADS) k_val(const KParams p) {
     const uint32_t count = *p.vq_count;
     unsigned long long pass = 0;
@@ -537,7 +541,8 @@ int sparc_env_create(SparcStore* store, int64_t n_envs, int traceback, int max_s
                 if (se == cudaSuccess) se = cudaMemset(e->vq_count, 0, 2 * sizeof(uint32_t));
                 int dev_sms = 0;
                 cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, store->device);
-                e->val_grid = dev_sms > 0 ? dev_sms : 148;
+                (void)dev_sms;
+                e->val_grid = 32;              // x128 threads; a small grid disturbs the co-running encoder least (measured)
             }
             if (se != cudaSuccess) { delete e; return fail(SPARC_E_CUDA, "side stream / queue: %s", cudaGetErrorString(se)); }
             e->split_chunks = nc;
