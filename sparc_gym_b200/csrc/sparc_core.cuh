@@ -477,22 +477,14 @@ SPARC_HD bool exact_fit(uint64_t region, int w, int h, const SparcShape* shapes,
     }
 }
 
-// ---- the validator in pieces (shared by the serial per-thread version and the warp-cooperative k_val) ----
-struct ValCtx {
-    HdrRegs h;
-    uint32_t Pm[8], C[8];            // passable nodes, rule cells (16-stride)
-    uint64_t STAR, SQ, SB0, SB1, COL[8], anycol;
-    const SparcShape* shapes;
-    int w, hh;                       // grid size in cells
-    int flags;                       // the five rules that need no regions
-};
-
 // vd: the env's visited plane in dense slab order, 9 readable words (word 8 may be anything
-// when S <= 256).  Fills the region-independent flags and everything the region pass needs.
-SPARC_HD void val_prologue(const StoreDev& st, uint32_t puzzle, const uint32_t* vd, int ax, int ay, ValCtx& c) {
-    c.h = load_hdr(st, puzzle);
+// when S <= 256).  region_map: optional int8[SX*SY] (row-major x, y), pre-filled with -1.
+SPARC_HD int validate_env(const StoreDev& st, uint32_t puzzle, const uint32_t* vd, int ax, int ay,
+                          int8_t* region_map) {
+    const HdrRegs h = load_hdr(st, puzzle);
     const uint32_t* nbp = st.nb + (size_t)puzzle * SPARC_N_NODE_BOARDS * 8;
-    uint32_t V[8];                                                              // visited: dense -> 16-stride
+    // visited: dense -> 16-stride
+    uint32_t V[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) V[k] = 0;
     const uint32_t rowmask = (1u << st.SY) - 1u;
@@ -503,12 +495,12 @@ SPARC_HD void val_prologue(const StoreDev& st, uint32_t puzzle, const uint32_t* 
 #pragma unroll
         for (int k = 0; k < 8; k++) V[k] |= (k == (x >> 1)) ? sh : 0u;
     }
-    uint32_t G[8], VAL[8], T[8];
+    uint32_t G[8], C[8], VAL[8], T[8];
     load_board(G, nbp + SPARC_NB_GAPS16 * 8);
-    load_board(c.C, nbp + SPARC_NB_CELL16 * 8);
+    load_board(C, nbp + SPARC_NB_CELL16 * 8);
     load_board(VAL, nbp + SPARC_NB_VALID16 * 8);
     int flags = 0;
-    if (ax == c.h.tx && ay == c.h.ty) flags |= SPARC_RULE_REACHED_TARGET;        // SG.py:488
+    if (ax == h.tx && ay == h.ty) flags |= SPARC_RULE_REACHED_TARGET;            // SG.py:488
     flags |= SPARC_RULE_PATH_NOT_CROSSING;      // path nodes are distinct by construction (SG.py:498)
     {                                                                           // SG.py:508, 521
         uint32_t gv = 0, dm = 0;
@@ -528,113 +520,36 @@ SPARC_HD void val_prologue(const StoreDev& st, uint32_t puzzle, const uint32_t* 
         for (int k = 0; k < 8; k++) {
             const uint32_t a = (V[k] << 16) | (k > 0 ? V[k - 1] >> 16 : 0u);   // node (x-1, y)
             const uint32_t b = (V[k] >> 16) | (k < 7 ? V[k + 1] << 16 : 0u);   // node (x+1, y)
-            const uint32_t cc = (V[k] << 1) & 0xFFFEFFFEu;                     // node (x, y-1)
+            const uint32_t c = (V[k] << 1) & 0xFFFEFFFEu;                      // node (x, y-1)
             const uint32_t d = (V[k] >> 1) & 0x7FFF7FFFu;                      // node (x, y+1)
-            const uint32_t s1 = a ^ b, c1 = a & b, s2 = cc ^ d, c2 = cc & d;
+            const uint32_t s1 = a ^ b, c1 = a & b, s2 = c ^ d, c2 = c & d;
             const uint32_t b0 = s1 ^ s2, cr = s1 & s2, b1 = c1 ^ c2 ^ cr, b2 = c1 & c2;
             const uint32_t eq1 = b0 & ~b1 & ~b2, eq2 = ~b0 & b1 & ~b2, eq3 = b0 & b1, eq4 = b2;
             bad |= (T1[k] & ~eq1) | (T2[k] & ~eq2) | (T3[k] & ~eq3) | (T4[k] & ~eq4) | T[k];
         }
         if (!bad) flags |= SPARC_RULE_TRIANGLES;
     }
-    c.flags = flags;
-    // regions (SG.py:422-454): passable = rule cell, or neither gap nor path (Q6)
+    // regions (SG.py:422-454): passable = rule cell, or neither gap nor path (Q6).  The three
+    // region rules are vacuously true for a puzzle without stars, squares and shape instances,
+    // so its region pass is skipped unless the caller wants the region map itself.
+    if (!(h.flags & 2) && !region_map) {
+        flags |= SPARC_RULE_SQUARES | SPARC_RULE_STARS | SPARC_RULE_POLY_YLOP;
+        if ((flags & 0xFF) == 0xFF) flags |= SPARC_RULE_ALL;
+        return flags;
+    }
+    uint32_t Pm[8], unl[8];
 #pragma unroll
-    for (int k = 0; k < 8; k++) c.Pm[k] = VAL[k] & (c.C[k] | ~(G[k] | V[k]));
+    for (int k = 0; k < 8; k++) { Pm[k] = VAL[k] & (C[k] | ~(G[k] | V[k])); unl[k] = C[k]; }
     const uint64_t* cbp = st.cb + (size_t)puzzle * SPARC_N_CELL_BOARDS;
-    c.STAR = sp_ldg(cbp + SPARC_CB_STAR); c.SQ = sp_ldg(cbp + SPARC_CB_SQUARE);
-    c.SB0 = sp_ldg(cbp + SPARC_CB_SYM1); c.SB1 = sp_ldg(cbp + SPARC_CB_SYM2);
-    c.anycol = 0;
+    const uint64_t STAR = sp_ldg(cbp + SPARC_CB_STAR), SQ = sp_ldg(cbp + SPARC_CB_SQUARE);
+    const uint64_t SB0 = sp_ldg(cbp + SPARC_CB_SYM1), SB1 = sp_ldg(cbp + SPARC_CB_SYM2);
+    uint64_t COL[8], anycol = 0;
 #pragma unroll
-    for (int k = 0; k < 8; k++) { c.COL[k] = sp_ldg(cbp + SPARC_CB_COLOR1 + k); c.anycol |= c.COL[k]; }
-    c.shapes = st.shapes + c.h.shape_off;
-    c.w = (c.h.X - 1) >> 1; c.hh = (c.h.Y - 1) >> 1;
-}
-
-// connected component of the passable nodes containing the seed (word k0, one bit) -> f
-SPARC_HD void val_flood(const uint32_t (&Pm)[8], int k0, uint32_t seed, uint32_t (&f)[8]) {
-#pragma unroll
-    for (int k = 0; k < 8; k++) f[k] = (k == k0) ? seed : 0u;
-    for (;;) {                                                                  // flood to fix-point
-        uint32_t g[8], ch = 0;
-#pragma unroll
-        for (int k = 0; k < 8; k++) g[k] = row_fill(Pm[k], f[k]);
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const uint32_t up = (g[k] << 16) | (k > 0 ? g[k - 1] >> 16 : 0u);
-            const uint32_t dn = (g[k] >> 16) | (k < 7 ? g[k + 1] << 16 : 0u);
-            const uint32_t nw = (g[k] | up | dn) & Pm[k];
-            ch |= nw ^ f[k];
-            f[k] = nw;
-        }
-        if (!ch) break;
-    }
-}
-// component (16-stride node board) -> rule-cell board
-SPARC_HD uint64_t val_cells(const uint32_t (&f)[8], const uint32_t (&C)[8]) {
-    uint64_t R = 0;
-#pragma unroll
-    for (int cx = 0; cx < 7; cx++) {
-        uint32_t t = ((f[cx] & C[cx]) >> 17) & 0x5555u;     // x = 2cx+1 is the high half; y odd -> even slots
-        t = (t | (t >> 1)) & 0x3333u; t = (t | (t >> 2)) & 0x0F0Fu; t = (t | (t >> 4)) & 0x00FFu;
-        R |= (uint64_t)t << (cx * 8);
-    }
-    return R;
-}
-// the three region rules on one region: bit mask of the VIOLATED rules
-SPARC_HD int val_region_rules(const ValCtx& c, uint64_t R) {
-    int bad = 0;
-    const uint64_t sq = c.SQ & R;                           // squares (SG.py:534-552)
-    if (sq) {
-        int nc = 0;
-#pragma unroll
-        for (int k = 0; k < 8; k++) nc += (sq & c.COL[k]) != 0;
-        if (nc > 1) bad |= SPARC_RULE_SQUARES;
-    }
-    const uint64_t sr = c.STAR & R;                         // stars (SG.py:554-614)
-    if (sr) {
-        if (sr & ~c.anycol) bad |= SPARC_RULE_STARS;        // colourless star (SG.py:580-582)
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            if (sr & c.COL[k]) {
-                const uint64_t rc = R & c.COL[k];
-                if (sp_popcll(c.SB0 & rc) + 2 * sp_popcll(c.SB1 & rc) != 2) bad |= SPARC_RULE_STARS;
-            }
-        }
-    }
-    if (c.h.n_shapes) {                                     // polys / ylops (SG.py:648-710)
-        uint8_t np[SPARC_MAX_SHAPES], nyl[SPARC_MAX_SHAPES];
-        int net = 0, any = 0;
-        for (int s = 0; s < c.h.n_shapes; s++) {
-            const int a = sp_popcll(sp_ldg(&c.shapes[s].poly_cells) & R), b = sp_popcll(sp_ldg(&c.shapes[s].ylop_cells) & R);
-            np[s] = (uint8_t)a; nyl[s] = (uint8_t)b; any |= a | b;
-            net += (a - b) * (int)c.shapes[s].area;
-        }
-        if (any) {
-            if (net != sp_popcll(R)) bad |= SPARC_RULE_POLY_YLOP;               // SG.py:679-682
-            else if (!exact_fit(R, c.w, c.hh, c.shapes, c.h.n_shapes, np, nyl)) bad |= SPARC_RULE_POLY_YLOP;
-        }
-    }
-    return bad;
-}
-SPARC_HD int val_finish(int flags, int bad) {
-    flags |= (SPARC_RULE_SQUARES | SPARC_RULE_STARS | SPARC_RULE_POLY_YLOP) & ~bad;
-    if ((flags & 0xFF) == 0xFF) flags |= SPARC_RULE_ALL;                        // SG.py:932-935
-    return flags;
-}
-
-// serial validator (one thread).  region_map: optional int8[SX*SY] (row-major x, y), pre-filled with -1.
-SPARC_HD int validate_env(const StoreDev& st, uint32_t puzzle, const uint32_t* vd, int ax, int ay,
-                          int8_t* region_map) {
-    ValCtx c;
-    val_prologue(st, puzzle, vd, ax, ay, c);
-    // The three region rules are vacuously true for a puzzle without stars, squares and shape
-    // instances, so its region pass is skipped unless the caller wants the region map itself.
-    if (!(c.h.flags & 2) && !region_map) return val_finish(c.flags, 0);
-    uint32_t unl[8];
-#pragma unroll
-    for (int k = 0; k < 8; k++) unl[k] = c.C[k];
-    int bad = 0, rid = 0;
+    for (int c = 0; c < 8; c++) { COL[c] = sp_ldg(cbp + SPARC_CB_COLOR1 + c); anycol |= COL[c]; }
+    const SparcShape* shapes = st.shapes + h.shape_off;
+    const int w = (h.X - 1) >> 1, hh = (h.Y - 1) >> 1;
+    bool sq_ok = true, star_ok = true, poly_ok = true;
+    int rid = 0;
     for (;;) {
         int k0 = -1;
 #pragma unroll
@@ -642,18 +557,77 @@ SPARC_HD int validate_env(const StoreDev& st, uint32_t puzzle, const uint32_t* v
         if (k0 < 0) break;
         uint32_t f[8];
         const uint32_t seed = board_word(unl, k0) & (0u - board_word(unl, k0));    // lowest set bit: raster order
-        val_flood(c.Pm, k0, seed, f);
 #pragma unroll
-        for (int k = 0; k < 8; k++) unl[k] &= ~(f[k] & c.C[k]);
-        const uint64_t R = val_cells(f, c.C);
+        for (int k = 0; k < 8; k++) f[k] = (k == k0) ? seed : 0u;
+        for (;;) {                                                              // flood to fix-point
+            uint32_t g[8], ch = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) g[k] = row_fill(Pm[k], f[k]);
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const uint32_t up = (g[k] << 16) | (k > 0 ? g[k - 1] >> 16 : 0u);
+                const uint32_t dn = (g[k] >> 16) | (k < 7 ? g[k + 1] << 16 : 0u);
+                const uint32_t nw = (g[k] | up | dn) & Pm[k];
+                ch |= nw ^ f[k];
+                f[k] = nw;
+            }
+            if (!ch) break;
+        }
+        uint64_t R = 0;                                     // component -> rule-cell board
+#pragma unroll
+        for (int cx = 0; cx < 7; cx++) {
+            const uint32_t cells = f[cx] & C[cx];
+            unl[cx] &= ~cells;
+            uint32_t t = (cells >> 17) & 0x5555u;           // x = 2cx+1 is the high half; y odd -> even slots
+            t = (t | (t >> 1)) & 0x3333u; t = (t | (t >> 2)) & 0x0F0Fu; t = (t | (t >> 4)) & 0x00FFu;
+            R |= (uint64_t)t << (cx * 8);
+        }
+        unl[7] &= ~(f[7] & C[7]);
         if (region_map) {
             uint64_t m = R;
             while (m) { const int b = sp_ffsll(m) - 1; m &= m - 1; region_map[(2 * (b >> 3) + 1) * st.SY + 2 * (b & 7) + 1] = (int8_t)rid; }
         }
-        bad |= val_region_rules(c, R);
+        // squares (SG.py:534-552): at most one distinct non-zero colour per region
+        const uint64_t sq = SQ & R;
+        if (sq) {
+            int nc = 0;
+#pragma unroll
+            for (int c = 0; c < 8; c++) nc += (sq & COL[c]) != 0;
+            if (nc > 1) sq_ok = false;
+        }
+        // stars (SG.py:554-614): every star colour must total exactly 2 symbols in the region
+        const uint64_t sr = STAR & R;
+        if (sr) {
+            if (sr & ~anycol) star_ok = false;              // colourless star (SG.py:580-582)
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                if (sr & COL[c]) {
+                    const uint64_t rc = R & COL[c];
+                    if (sp_popcll(SB0 & rc) + 2 * sp_popcll(SB1 & rc) != 2) star_ok = false;
+                }
+            }
+        }
+        // polys / ylops (SG.py:648-710)
+        if (h.n_shapes && poly_ok) {
+            uint8_t np[SPARC_MAX_SHAPES], nyl[SPARC_MAX_SHAPES];
+            int net = 0, any = 0;
+            for (int s = 0; s < h.n_shapes; s++) {
+                const int a = sp_popcll(sp_ldg(&shapes[s].poly_cells) & R), b = sp_popcll(sp_ldg(&shapes[s].ylop_cells) & R);
+                np[s] = (uint8_t)a; nyl[s] = (uint8_t)b; any |= a | b;
+                net += (a - b) * (int)shapes[s].area;
+            }
+            if (any) {
+                if (net != sp_popcll(R)) poly_ok = false;   // SG.py:679-682
+                else if (!exact_fit(R, w, hh, shapes, h.n_shapes, np, nyl)) poly_ok = false;
+            }
+        }
         rid++;
     }
-    return val_finish(c.flags, bad);
+    if (sq_ok) flags |= SPARC_RULE_SQUARES;
+    if (star_ok) flags |= SPARC_RULE_STARS;
+    if (poly_ok) flags |= SPARC_RULE_POLY_YLOP;
+    if ((flags & 0xFF) == 0xFF) flags |= SPARC_RULE_ALL;                        // SG.py:932-935
+    return flags;
 }
 
 // ---------------------------------------------------------------------------------------------
