@@ -114,7 +114,8 @@ typedef struct {                 /* 32 bytes */
     uint8_t  area;               /* sum of the shape array (SG.py:733) */
     uint8_t  anchor_dy;          /* -min_dy: anchor column inside `mask` */
     uint8_t  max_dx, span_y;     /* extent of `mask` */
-    uint8_t  flags;              /* bit0: cannot be placed on any 7x7 grid; bit1: no filled entry */
+    uint8_t  flags;              /* bit0: cannot be placed on any 7x7 grid; bit1: no filled entry;
+                                    bit2: the filled entries are 4-connected */
     uint8_t  pad[3];
 } SparcShape;
 

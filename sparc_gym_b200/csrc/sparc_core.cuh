@@ -314,7 +314,7 @@ SPARC_HD void cnt_add(Cnt3& c, uint64_t m) { uint64_t t = c.c0 & m; c.c0 ^= m; m
 SPARC_HD void cnt_sub(Cnt3& c, uint64_t m) { uint64_t t = ~c.c0 & m; c.c0 ^= m; m = t; t = ~c.c1 & m; c.c1 ^= m; c.c2 ^= t; }
 
 SPARC_HD uint64_t shape_place(const SparcShape& s, int cx, int cy, int w, int h) {
-    if (s.flags) return 0;                                  // unplaceable / empty
+    if (s.flags & 3) return 0;                              // unplaceable / empty
     const int y0 = cy - (int)s.anchor_dy;
     if (y0 < 0 || cx + (int)s.max_dx >= w || y0 + (int)s.span_y >= h) return 0;   // SG.py:880-883
     return s.mask << (cx * 8 + y0);
@@ -422,16 +422,25 @@ SPARC_HD bool exact_fit(uint64_t region, int w, int h, const SparcShape* shapes,
         tot_p += rem_p[s]; tot_y += rem_y[s];
     }
     if (tot_y > SPARC_MAX_YLOPS) return false;                // (ingest guarantees this never happens)
+    // isolated-cell prune: once no ylop is left, a demanded cell with no demanded 4-neighbour can only be
+    // covered by a one-cell poly (every other shape is 4-connected and would need a neighbour)
+    uint32_t mono_slots = 0;
+    bool all_connected = true;
+    for (int s = 0; s < ns; s++) {
+        if (rem_p[s] && !(shapes[s].flags & 4)) all_connected = false;
+        if (shapes[s].mask == 1ull) mono_slots |= 1u << s;
+    }
     Cnt4 c = {region, 0, 0, 0};
     uint64_t grid = 0;
     for (int cx = 0; cx < w; cx++) grid |= ((1ull << h) - 1ull) << (cx * 8);
     int level = 0, cell = 0, q = 0;
+    if (tot_y == 0) cell = sp_ffsll(region) - 1;              // no ylops: only demanded cells ever matter
     for (;;) {
         SPARC_COUNT_FIT();
         const int n = cnt4_get(c, cell);
         const uint64_t later = grid & ~((2ull << cell) - 1ull);               // cells after `cell`
         bool found = false;
-        for (int qq = q; qq < 2 * ns; qq++) {
+        for (int qq = (tot_y == 0 && q < ns) ? ns : q; qq < 2 * ns; qq++) {
             if (qq < ns) {                                                    // anchor a ylop here
                 if (!rem_y[qq] || n + 1 > tot_p) continue;
                 const uint64_t m = shape_place(shapes[qq], cell >> 3, cell & 7, w, h);
@@ -447,6 +456,15 @@ SPARC_HD bool exact_fit(uint64_t region, int w, int h, const SparcShape* shapes,
                 if (!m) continue;
                 if (cnt4_eq(c, -tot_y) & later & m) continue;                 // would sink below what ylops can lift
                 cnt4_sub(c, m); rem_p[s]--; tot_p--;
+                if (tot_y == 0 && all_connected) {
+                    const uint64_t D = (c.b0 | c.b1 | c.b2) & ~c.b3;          // cells still demanded
+                    const uint64_t iso = D & ~((D << 1) | (D >> 1) | (D << 8) | (D >> 8));
+                    if (iso) {
+                        int monos = 0;
+                        for (uint32_t ms = mono_slots; ms; ms &= ms - 1) monos += rem_p[sp_ffs(ms) - 1];
+                        if (sp_popcll(iso) > monos) { cnt4_add(c, m); rem_p[s]++; tot_p++; continue; }
+                    }
+                }
             }
             fr_cell[level] = (uint8_t)cell; fr_q[level] = (uint8_t)qq; level++;
             q = qq; found = true;
@@ -454,12 +472,13 @@ SPARC_HD bool exact_fit(uint64_t region, int w, int h, const SparcShape* shapes,
         }
         if (found) continue;
         if (cnt4_get(c, cell) == 0) {                                         // settled: advance
-            if (!later) { if (tot_p == 0 && tot_y == 0) return true; }
-            else if (tot_p + tot_y == 0) {
-                if (((c.b0 | c.b1 | c.b2 | c.b3) & later) == 0) return true;  // nothing left and nothing demanded
-            } else {
+            const uint64_t open = (c.b0 | c.b1 | c.b2 | c.b3) & later;        // later cells with non-zero demand
+            if (tot_p + tot_y == 0) { if (!open) return true; }               // nothing left and nothing demanded
+            else if (later && (tot_y > 0 || open)) {
+                // with ylops still to place every later cell is a candidate anchor; without, only a
+                // demanded cell can take a poly, so jump straight to the next one
                 fr_cell[level] = (uint8_t)cell; fr_q[level] = 0xFF; level++;
-                cell = sp_ffsll(later) - 1; q = 0;
+                cell = sp_ffsll(tot_y > 0 ? later : open) - 1; q = 0;
                 continue;
             }
         }
@@ -977,6 +996,9 @@ SPARC_HD int validate_queued(const KParams& p, uint32_t slot) {
 #pragma unroll
     for (int k = 0; k < 8; k++) vd[k] = q[4 + k];
     vd[8] = 0;
+#ifdef VAL_SKIP_HEAVY      /* timing experiment only: pretend long paths need no validation */
+    { int pc = 0; for (int k = 0; k < 8; k++) pc += sp_popc(vd[k]); if (pc > VAL_SKIP_HEAVY) return 0; }
+#endif
     const int f = validate_env(p.st, q[1], vd, (int)(q[2] & 0xff), (int)((q[2] >> 8) & 0xff), nullptr) | SPARC_RULE_VALID;
     if (p.out.rule_flags_dev) p.out.rule_flags_dev[q[0]] = (uint16_t)f;
     return (f & SPARC_RULE_ALL) != 0;

@@ -90,6 +90,17 @@ def shape_slot(arr):
     for i, j in zip(dx.tolist(), (dy - min_dy).tolist()):
         m |= 1 << (i * 8 + j)
     rec["mask"] = m
+    # bit2: the filled entries are 4-connected (lets the exact-fit search prune isolated cells)
+    cells = set(zip(dx.tolist(), (dy - min_dy).tolist()))
+    seen, todo = set(), [next(iter(cells))]
+    while todo:
+        c = todo.pop()
+        if c in seen:
+            continue
+        seen.add(c)
+        todo += [n for n in ((c[0] + 1, c[1]), (c[0] - 1, c[1]), (c[0], c[1] + 1), (c[0], c[1] - 1)) if n in cells]
+    if seen == cells:
+        rec["flags"] = int(rec["flags"]) | 4
     return rec
 
 
