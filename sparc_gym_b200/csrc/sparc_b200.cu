@@ -45,6 +45,9 @@ struct SparcEnv {
     int enc_tile;            // envs per k_encode CTA
     cudaStream_t side;       // high-priority stream of k_dyn (multi-chunk) / k_val
     cudaEvent_t ev_start, ev_dyn[16], ev_val;
+    cudaStream_t copy_stream;   // sparc_step_host: result copies run beside k_encode
+    cudaEvent_t ev_dyn_done, ev_copy;
+    struct { float* reward; uint8_t* term; uint8_t* trunc; bool active; } hostcopy;
     uint32_t* vq_count;      // deferred-validation queue (split path, validate = terminal)
     uint32_t* vq;
     int val_grid;
@@ -153,6 +156,10 @@ __global__ void __launch_bounds__(ENC_THREADS, ENC_MINBLOCKS) k_encode(const KPa
     const int nE = (int)min((long long)p.tile, hi - env0);
     uint32_t* head = smem;
     uint32_t* flats = smem + tile_head_words(p.tile);
+#ifdef ENC_SKIP_STAGE1      /* timing experiment only (wrong output): how fast is the expand loop alone? */
+    if (tid < nE) head[p.tile * SPARC_DYN_STRIDE + tid] = 0;
+    __syncthreads();
+#else
     if (tid < nE) {
         EnvRegs e;
         load_env(e, p.sd, st, p.cfg.n_envs, env0 + tid);
@@ -165,6 +172,7 @@ __global__ void __launch_bounds__(ENC_THREADS, ENC_MINBLOCKS) k_encode(const KPa
     __syncthreads();
     encode_tile_stage1b(st, head, flats, p.tile, nE, p.obs, tid, ENC_THREADS);
     __syncthreads();
+#endif
     encode_tile_stage2(st, head, flats, p.tile, nE, env0, p.obs, tid, ENC_THREADS);
 }
 
@@ -534,6 +542,9 @@ int sparc_env_create(SparcStore* store, int64_t n_envs, int traceback, int max_s
             if (se == cudaSuccess) se = cudaEventCreateWithFlags(&e->ev_start, cudaEventDisableTiming);
             for (int c = 0; c < nc && se == cudaSuccess; c++) se = cudaEventCreateWithFlags(&e->ev_dyn[c], cudaEventDisableTiming);
             if (se == cudaSuccess) se = cudaEventCreateWithFlags(&e->ev_val, cudaEventDisableTiming);
+            if (se == cudaSuccess) se = cudaStreamCreateWithPriority(&e->copy_stream, cudaStreamNonBlocking, hi_p);
+            if (se == cudaSuccess) se = cudaEventCreateWithFlags(&e->ev_dyn_done, cudaEventDisableTiming);
+            if (se == cudaSuccess) se = cudaEventCreateWithFlags(&e->ev_copy, cudaEventDisableTiming);
             const char* de = getenv("SPARC_DEFER_VALIDATION");
             if (se == cudaSuccess && !(de && atoi(de) == 0)) {
                 se = cudaMalloc((void**)&e->vq_count, 2 * sizeof(uint32_t));   // count, finished k_val CTAs
@@ -592,6 +603,9 @@ int sparc_env_destroy(SparcEnv* e) {
     if (e->ev_start) cudaEventDestroy(e->ev_start);
     for (cudaEvent_t ev : e->ev_dyn) if (ev) cudaEventDestroy(ev);
     if (e->ev_val) cudaEventDestroy(e->ev_val);
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+    if (e->ev_dyn_done) cudaEventDestroy(e->ev_dyn_done);
+    if (e->ev_copy) cudaEventDestroy(e->ev_copy);
     delete e;
     return SPARC_OK;
 }
@@ -627,6 +641,15 @@ static int launch_env(SparcEnv* e, KParams& p, void* stream) {
                 CU(cudaEventRecord(e->ev_dyn[c], e->side));
                 CU(cudaStreamWaitEvent(s0, e->ev_dyn[c], 0));
             }
+            if (e->hostcopy.active && nc == 1) {                             // fork: results -> host beside k_encode
+                const size_t nn = (size_t)n;
+                CU(cudaEventRecord(e->ev_dyn_done, s0));
+                CU(cudaStreamWaitEvent(e->copy_stream, e->ev_dyn_done, 0));
+                if (e->hostcopy.reward) CU(cudaMemcpyAsync(e->hostcopy.reward, e->rew_stage, nn * 4, cudaMemcpyDeviceToHost, e->copy_stream));
+                if (e->hostcopy.term) CU(cudaMemcpyAsync(e->hostcopy.term, e->term_stage, nn, cudaMemcpyDeviceToHost, e->copy_stream));
+                if (e->hostcopy.trunc) CU(cudaMemcpyAsync(e->hostcopy.trunc, e->trunc_stage, nn, cudaMemcpyDeviceToHost, e->copy_stream));
+                CU(cudaEventRecord(e->ev_copy, e->copy_stream));
+            }
             if (defer) {                                                     // fork: k_val beside k_encode
                 CU(cudaEventRecord(e->ev_start, s0));
                 CU(cudaStreamWaitEvent(e->side, e->ev_start, 0));
@@ -636,6 +659,7 @@ static int launch_env(SparcEnv* e, KParams& p, void* stream) {
             }
             if (any_obs) k_encode<<<(unsigned)((hi - lo + p.tile - 1) / p.tile), ENC_THREADS, shmem, s0>>>(p, lo, hi);
             if (defer) CU(cudaStreamWaitEvent(s0, e->ev_val, 0));            // join
+            if (e->hostcopy.active && nc == 1) CU(cudaStreamWaitEvent(s0, e->ev_copy, 0));
             e->launches += any_obs ? 2 : 1;
         }
         CU(cudaGetLastError());
@@ -713,11 +737,17 @@ int sparc_step_host(SparcEnv* e, const uint8_t* actions_host, float* reward_host
     CU(cudaMemcpyAsync(e->act_stage, actions_host, n, cudaMemcpyHostToDevice, s));
     SparcStepOut out; memset(&out, 0, sizeof(out));
     out.reward_dev = e->rew_stage; out.terminated_dev = e->term_stage; out.truncated_dev = e->trunc_stage;
+    // big batches: the result copies are issued right behind k_dyn on a side stream and overlap k_encode
+    const bool overlap = e->split_chunks == 1 && e->copy_stream;
+    if (overlap) { e->hostcopy.reward = reward_host; e->hostcopy.term = terminated_host; e->hostcopy.trunc = truncated_host; e->hostcopy.active = true; }
     int rc = sparc_step(e, e->act_stage, SPARC_ACT_U8, &out, obs, stream);
+    e->hostcopy.active = false;
     if (rc) return rc;
-    if (reward_host) CU(cudaMemcpyAsync(reward_host, e->rew_stage, n * 4, cudaMemcpyDeviceToHost, s));
-    if (terminated_host) CU(cudaMemcpyAsync(terminated_host, e->term_stage, n, cudaMemcpyDeviceToHost, s));
-    if (truncated_host) CU(cudaMemcpyAsync(truncated_host, e->trunc_stage, n, cudaMemcpyDeviceToHost, s));
+    if (!overlap) {
+        if (reward_host) CU(cudaMemcpyAsync(reward_host, e->rew_stage, n * 4, cudaMemcpyDeviceToHost, s));
+        if (terminated_host) CU(cudaMemcpyAsync(terminated_host, e->term_stage, n, cudaMemcpyDeviceToHost, s));
+        if (truncated_host) CU(cudaMemcpyAsync(truncated_host, e->trunc_stage, n, cudaMemcpyDeviceToHost, s));
+    }
     CU(cudaStreamSynchronize(s));
     return SPARC_OK;
 }

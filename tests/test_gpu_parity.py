@@ -105,3 +105,23 @@ def test_checkpoint_restore_and_standalone_encode():
         ra, rb = a.step(acts[t]), b.step(acts[t])
         assert torch.equal(ra[1], rb[1]) and torch.equal(ra[2], rb[2]) and torch.equal(ra[3], rb[3])
         assert all(torch.equal(ra[0][k], rb[0][k]) for k in ra[0])
+
+
+def test_step_host_matches_device_step():
+    """sparc_step_host (host action / result buffers, result copies overlapped with the encoder on the
+    split path) returns exactly what the device-buffer step returns."""
+    rows = gen_pool(16, [(4, 4), (6, 6)], RULES_FULL, seed0=500)
+    for n in (40000, 300):                      # split pipeline / fused kernel
+        a = make_env(rows, n, traceback=False, max_steps=20, autoreset_mode="same_step")
+        b = make_env(rows, n, traceback=False, max_steps=20, autoreset_mode="same_step")
+        a.reset(); b.reset()
+        rng = np.random.default_rng(n)
+        r = torch.empty(n, dtype=torch.float32).pin_memory()
+        te = torch.empty(n, dtype=torch.uint8).pin_memory()
+        tr = torch.empty(n, dtype=torch.uint8).pin_memory()
+        for t in range(30):
+            act = torch.from_numpy(rng.integers(0, 4, n).astype(np.uint8))
+            a.step_host(act.pin_memory(), r, te, tr)
+            ob, rb, tb, ub, _ = b.step(act.cuda())
+            assert torch.equal(r, rb.cpu()) and torch.equal(te, tb.cpu()) and torch.equal(tr, ub.cpu()), (n, t)
+            assert all(torch.equal(a.obs[k], ob[k]) for k in ob)
