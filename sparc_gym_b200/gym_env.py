@@ -11,8 +11,8 @@ int64[X, Y]}` and the arrays are owned by the env and updated in place (SG.py:97
 All dynamics, rewards, rule validation and the observation planes come from the CUDA library
 (one env on the GPU); this class only converts device arrays into the reference's containers.
 Deliberate differences: resets are clean, `info['rule_status'][rule]['detail']` is
-reduced to what the device computes, there are no pygame renderers, and only observation='new'
-is implemented on the device.
+reduced to what the device computes, and there are no pygame renderers.  observation='SPaRC'
+(the JSON text grid, SG.py:1149-1184) is assembled on the host from the device's dynamics.
 """
 from __future__ import annotations
 
@@ -66,9 +66,8 @@ class SPaRC_Gym(_Env):
 
     def __init__(self, df_name="lkaesberg/SPaRC", df_split="all", df_set="test", render_mode=None,
                  observation="new", traceback=False, max_steps=2000, *, puzzles=None, device="cuda:0"):
-        if observation != "new":
-            raise ValueError("Invalid observation type. Choose 'new' or 'SPaRC'." if observation != "SPaRC" else
-                             "observation='SPaRC' (JSON text) is not implemented on the B200 path yet")
+        if observation not in ("new", "SPaRC"):
+            raise ValueError("Invalid observation type. Choose 'new' or 'SPaRC'.")     # SG.py:207
         if render_mode is not None:
             raise ValueError("the B200 environment has no renderers (render_mode must be None)")
         from .vec_env import SparcVecEnv
@@ -77,7 +76,7 @@ class SPaRC_Gym(_Env):
         rows = puzzles if puzzles is not None else _load_rows(df_name, df_split, df_set)
         if rows is None or len(rows) == 0:
             raise ValueError("No valid dataframe provided")                    # SG.py:86-87
-        self.puzzles = ingest_rows(rows)
+        self.puzzles = ingest_rows(rows, observation)
         self._store = PuzzleStore(self.puzzles)
         self._vec = SparcVecEnv(self._store, 1, traceback=traceback, max_steps=max_steps,
                                 autoreset_mode="disabled", validate="never", device=device)   # _pull() validates on demand
@@ -106,6 +105,14 @@ class SPaRC_Gym(_Env):
         self._agent_location = np.zeros(2, np.int32)
         self._target_location = np.array(pz.target, dtype=np.int32)
         self._pull()
+        if self.observation == "SPaRC":                                        # SG.py:153-164, 198-204
+            self.observ = [[str(c) for c in row] for row in pz.observ]
+            if any(len(r) != len(self.observ[0]) for r in self.observ):
+                raise ValueError("Non-rectangular SPaRC grid")
+            init_json = self._build_json_obs()
+            self.observation_space = _spaces.Text(max_length=int(len(init_json) * 2),
+                                                  charset="".join(sorted(set(init_json) | set("LV."))))
+            return
         keys = list(self.obs_array.keys())
         self.observation_space = _spaces.Dict({                                # SG.py:190-196
             "base": _spaces.Dict({k: _spaces.Box(low=0, high=1, shape=(pz.X, pz.Y), dtype=np.int32) for k in keys}),
@@ -148,7 +155,13 @@ class SPaRC_Gym(_Env):
                     out[rid]["colors"][c] = out[rid]["colors"].get(c, 0) + 1
         return out
 
-    def _get_obs(self):                                                         # SG.py:956-979
+    def _build_json_obs(self):                                                  # SG.py:988-992
+        import json
+        return json.dumps(self.observ, separators=(",", ":"))
+
+    def _get_obs(self):                                                         # SG.py:956-983
+        if self.observation == "SPaRC":
+            return self._build_json_obs()
         return {"base": self.obs_array, "color": self.color_array, "additional_info": self.additional_info}
 
     def _get_info(self):                                                        # SG.py:994-1022
@@ -190,12 +203,21 @@ class SPaRC_Gym(_Env):
         v = self._vec
         if int(v.terminated[0]) or int(v.truncated[0]):
             raise RuntimeError("episode is over: call reset() (the B200 env does not step finished episodes, SURVEY Q4)")
+        old = (int(self._agent_location[0]), int(self._agent_location[1]))
+        old_len = int(self.obs_array["visited"].sum())
         v.step(torch.tensor([a], dtype=torch.int64))
         code = int(v.reward_code[0])
         terminated, truncated = bool(int(v.terminated[0])), bool(int(v.truncated[0]))
         self.normal_reward = abi.REWARD_VALUES[code]                            # ints 0/1/-1, floats +-0.01
         self.outcome_reward = {3: 1, 4: -1}.get(code, 0)                        # SG.py:1204-1215
         self._pull()
+        new = (int(self._agent_location[0]), int(self._agent_location[1]))
+        if self.observation == "SPaRC" and new != old:                          # text overlays, SG.py:1149-1184
+            if int(self.obs_array["visited"].sum()) < old_len:                  # traceback undo restores the node
+                self.observ[old[1]][old[0]] = "." if self.obs_array["gaps"][old] == 1 else "+"
+            else:
+                self.observ[old[1]][old[0]] = "V"
+            self.observ[new[1]][new[0]] = "L"
         return self._get_obs(), self.normal_reward, terminated, truncated, self._get_info()
 
     def render(self):                                                           # SG.py:1269-1299

@@ -8,6 +8,7 @@ Outputs (committed; the GPU box has no /root/reference):
   polyfit.json.gz   direct known answers of the reference's exact-fit search
   resets.json.gz    puzzle-cursor behaviour of reset(seed=...) / reset() / reset(options=...)
   ingest.json.gz    `_process_puzzles` results on rows that exercise the ingest quirks
+  sparc_text.json.gz  observation='SPaRC' strings, step by step
 """
 from __future__ import annotations
 
@@ -199,9 +200,33 @@ def make_ingest():
     dump("ingest.json.gz", out)
 
 
+def make_sparc_text():
+    """observation='SPaRC' (JSON text of the [y][x] symbol grid with L / V / + / . overlays, SG.py:1149-1184)."""
+    rows = [gen_puzzle(3, 3, 31, RULES_FULL), gen_puzzle(4, 4, 32, RULES_FULL), gen_puzzle(5, 4, 33, RULES_FULL)]
+    episodes = []
+    for tb in (False, True):
+        ref = rh.make_reference_env(rows, observation="SPaRC", traceback=tb, max_steps=30)
+        for i, row in enumerate(rows):
+            for ep in range(2):
+                acts = fuzz_actions(row, 77 * i + ep + 10 * tb, 35, p_follow=0.5 if ep else 0.95, n_act=4)
+                rh.zero_leak(ref)
+                obs, info = ref.reset(options={"puzzle_id": row["id"]})
+                trace = [[obs, None, None, None, [int(a) for a in info["legal_actions"]]]]
+                used = []
+                for a in acts:
+                    obs, r, te, tr, info = ref.step(a)
+                    used.append(a)
+                    trace.append([obs, [type(r).__name__, float(r)], bool(te), bool(tr), [int(x) for x in info["legal_actions"]]])
+                    if te or tr:
+                        break
+                episodes.append({"row": i, "traceback": tb, "max_steps": 30, "actions": used, "trace": trace})
+    dump("sparc_text.json.gz", {"rows": rows, "episodes": episodes})
+
+
 if __name__ == "__main__":
     if not rh.reference_available():
         sys.exit("reference not present; golden vectors can only be regenerated in the build container")
+    make_sparc_text()
     make_ingest()
     make_resets()
     make_polyfit()

@@ -46,3 +46,22 @@ def test_reset_cursor_matches_reference():
         else:
             env.reset(seed=s[1], options={"puzzle_id": s[2]})
         assert env.current_puzzle_index == want, s
+
+
+def test_dropin_sparc_text_observation_matches_reference():
+    """observation='SPaRC': the JSON text grid with its L / V / + / . overlays, step by step."""
+    import sparc_gym_b200
+    with gzip.open(os.path.join(G, "sparc_text.json.gz"), "rb") as f:
+        g = json.loads(f.read())
+    envs = {}
+    for ep in g["episodes"]:
+        key = (ep["traceback"], ep["max_steps"])
+        if key not in envs:
+            envs[key] = sparc_gym_b200.make("SPaRC-Gym", puzzles=g["rows"], observation="SPaRC",
+                                            traceback=key[0], max_steps=key[1])
+        env = envs[key]
+        obs, info = env.reset(options={"puzzle_id": g["rows"][ep["row"]]["id"]})
+        assert [obs, None, None, None, info["legal_actions"]] == ep["trace"][0]
+        for a, want in zip(ep["actions"], ep["trace"][1:]):
+            obs, r, te, tr, info = env.step(a)
+            assert [obs, [type(r).__name__, float(r)], te, tr, info["legal_actions"]] == want

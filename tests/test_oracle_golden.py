@@ -96,3 +96,18 @@ def test_state_leak_mode_reproduces_q1():
     clean = so.OracleEnv(g["rows"][:1], max_steps=10)
     obs, _ = clean.reset(options={"puzzle_id": g["rows"][0]["id"]})
     assert int(obs["base"]["visited"].sum()) == 1 and int(obs["base"]["agent_location"].sum()) == 1
+
+
+def test_sparc_text_observation_matches_reference():
+    g = load("sparc_text.json.gz")
+    envs = {}
+    for ep in g["episodes"]:
+        key = (ep["traceback"], ep["max_steps"])
+        if key not in envs:
+            envs[key] = so.OracleEnv(g["rows"], observation="SPaRC", traceback=key[0], max_steps=key[1])
+        env = envs[key]
+        obs, info = env.reset(options={"puzzle_id": g["rows"][ep["row"]]["id"]})
+        assert [obs, None, None, None, info["legal_actions"]] == ep["trace"][0]
+        for a, want in zip(ep["actions"], ep["trace"][1:]):
+            obs, r, te, tr, info = env.step(a)
+            assert [obs, [type(r).__name__, float(r)], te, tr, info["legal_actions"]] == want
