@@ -47,7 +47,8 @@ int emu_launch(const SparcStoreDesc* desc, uint32_t* core, uint32_t* vis, int32_
     uint32_t vq_count = 0;
     if (defer_validation) { vq.resize((size_t)n_envs * SPARC_VQ_WORDS); p.vq = vq.data(); p.vq_count = &vq_count; }
     const StoreDev& st = p.st;
-    std::vector<uint32_t> smem((size_t)tile_head_words(tile) + tile_flat_words(st, tile) + 4, 0xDEADBEEFu);
+    // exactly the dynamic shared memory the kernels request: an out-of-bounds row access is an ASan error
+    std::vector<uint32_t> smem((size_t)tile_head_words(tile) + tile_flat_words(st, tile), 0xDEADBEEFu);
     std::vector<EnvRegs> regs(tile);
     for (long long env0 = 0; env0 < n_envs; env0 += tile) {
         const int nE = (int)((n_envs - env0) < tile ? (n_envs - env0) : tile);

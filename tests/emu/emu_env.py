@@ -18,6 +18,8 @@ LIB = os.path.join(HERE, "libsparc_emu.so")
 
 
 def build_emu():
+    if os.environ.get("SPARC_EMU_LIB"):          # e.g. the ASan/UBSan build of tests/test_emu_sanitizers.py
+        return os.environ["SPARC_EMU_LIB"]
     src = os.path.join(HERE, "emu.cpp")
     deps = [src, os.path.join(abi.CSRC, "sparc_core.cuh"), os.path.join(abi.REPO_ROOT, "include", "sparc_b200.h")]
     if os.path.exists(LIB) and os.path.getmtime(LIB) >= max(os.path.getmtime(d) for d in deps):
