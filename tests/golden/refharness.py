@@ -90,13 +90,16 @@ def load_reference_class():
         import pygame  # noqa: F401
     except ImportError:
         sys.modules["pygame"] = types.ModuleType("pygame")
-    if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
+    # Load the reference's engine module under a private package name, straight from its files: the
+    # repo ships its own `SPaRC_Gym` import shim, which must not shadow (or be shadowed by) the reference.
     import importlib
-    importlib.import_module("SPaRC_Gym")
-    # the package __init__ rebinds the name `SPaRC_Gym.SPaRC_Gym` to the class; the module
-    # itself (where `load_dataset` must be patched) is in sys.modules
-    return sys.modules["SPaRC_Gym.SPaRC_Gym"]
+    name = "_sparc_reference"
+    if name + ".SPaRC_Gym" not in sys.modules:
+        pkg = types.ModuleType(name)
+        pkg.__path__ = [os.path.join(REFERENCE_ROOT, "SPaRC_Gym")]
+        sys.modules[name] = pkg
+        importlib.import_module(name + ".SPaRC_Gym")       # its `from .render import ...` resolves inside pkg.__path__
+    return sys.modules[name + ".SPaRC_Gym"]
 
 
 def make_reference_env(rows, **kwargs):

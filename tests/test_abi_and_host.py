@@ -142,3 +142,27 @@ def test_stats_reduction_over_gloo_world_size_2():
     mp.spawn(_gloo_worker, args=(2, port, out), nprocs=2, join=True)
     want = {n: k * 1 + (k * 2 - 5) for k, n in enumerate(abi.STAT_NAMES)}
     assert dict(out[0]) == want and dict(out[1]) == want
+
+
+def test_rows_survive_a_parquet_round_trip(tmp_path):
+    """Real SPaRC rows arrive as pandas/pyarrow objects (numpy arrays of dicts, numpy scalars): the
+    loader + ingest must give the same planes as the plain-Python rows."""
+    import pandas as pd
+    from sparc_gym_b200.dataset import load_rows
+    rows = gen_pool(5, [(3, 3), (5, 5)], RULES_FULL, seed0=31) + [fuzz_row(s) for s in range(600, 605)]
+    for r in rows:
+        r.pop("puzzle_array", None)            # ragged object column; only observation='SPaRC' reads it
+    path = tmp_path / "sparc.parquet"
+    pd.DataFrame(rows).to_parquet(path)
+    back = load_rows(path)
+    a, b = ingest_rows(rows), ingest_rows(back)
+    sa, sb = PuzzleStore(a), PuzzleStore(b)
+    for name in ("headers", "node_boards", "cell_boards", "static_bits", "color4", "info_nz", "info", "shapes", "trie"):
+        assert np.array_equal(getattr(sa, name), getattr(sb, name)), name
+    assert [p.keys for p in a] == [p.keys for p in b]
+
+
+def test_import_compat_shim():
+    import SPaRC_Gym as shim
+    import sparc_gym_b200
+    assert shim.SPaRC_Gym is sparc_gym_b200.SPaRC_Gym
