@@ -623,7 +623,7 @@ static int launch_env(SparcEnv* e, KParams& p, void* stream) {
         p.tile = e->enc_tile;
         const size_t shmem = (size_t)(tile_head_words(p.tile) + tile_flat_words(p.st, p.tile)) * sizeof(uint32_t);
         cudaStream_t sd = nc > 1 ? e->side : s0;                         // one chunk: plain back-to-back launches
-        const bool defer = nc == 1 && p.mode == 0 && e->vq && e->cfg.validate_mode == SPARC_VALIDATE_TERMINAL;
+        const bool defer = p.mode == 0 && e->vq && e->cfg.validate_mode == SPARC_VALIDATE_TERMINAL;
         if (defer) {
             p.vq = e->vq; p.vq_count = e->vq_count;                     // (k_val leaves the queue empty)
         }
@@ -650,15 +650,18 @@ static int launch_env(SparcEnv* e, KParams& p, void* stream) {
                 if (e->hostcopy.trunc) CU(cudaMemcpyAsync(e->hostcopy.trunc, e->trunc_stage, nn, cudaMemcpyDeviceToHost, e->copy_stream));
                 CU(cudaEventRecord(e->ev_copy, e->copy_stream));
             }
-            if (defer) {                                                     // fork: k_val beside k_encode
-                CU(cudaEventRecord(e->ev_start, s0));
-                CU(cudaStreamWaitEvent(e->side, e->ev_start, 0));
+            const bool last = hi >= n;
+            if (defer && last) {                                             // fork: k_val beside (the last) k_encode
+                if (nc == 1) {
+                    CU(cudaEventRecord(e->ev_start, s0));
+                    CU(cudaStreamWaitEvent(e->side, e->ev_start, 0));
+                }
                 k_val<<<(unsigned)e->val_grid, CTA_THREADS, 0, e->side>>>(p);
                 CU(cudaEventRecord(e->ev_val, e->side));
                 e->launches++;
             }
             if (any_obs) k_encode<<<(unsigned)((hi - lo + p.tile - 1) / p.tile), ENC_THREADS, shmem, s0>>>(p, lo, hi);
-            if (defer) CU(cudaStreamWaitEvent(s0, e->ev_val, 0));            // join
+            if (defer && last) CU(cudaStreamWaitEvent(s0, e->ev_val, 0));    // join
             if (e->hostcopy.active && nc == 1) CU(cudaStreamWaitEvent(s0, e->ev_copy, 0));
             e->launches += any_obs ? 2 : 1;
         }
