@@ -530,7 +530,8 @@ int sparc_env_create(SparcStore* store, int64_t n_envs, int traceback, int max_s
     }
     {   // big batches: the k_dyn || k_encode pipeline
         const char* pe = getenv("SPARC_SPLIT");                // chunks; 0 = fused k_env; unset = automatic
-        int nc = pe ? atoi(pe) : (n_envs >= 32768 ? 1 : 0);   // measured: 1 chunk (k_dyn then k_encode) is fastest
+        int nc = pe ? atoi(pe) : (n_envs >= 8192 ? 1 : 0);    // measured crossover with the fused k_env: ~6 k envs;
+                                                               // 1 chunk (k_dyn, then k_val || k_encode) beats 2..8 chunks
         if (nc > 16) nc = 16;
         const char* te = getenv("SPARC_ENC_TILE");
         e->enc_tile = te ? atoi(te) : 8;
