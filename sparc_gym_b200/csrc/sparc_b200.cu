@@ -1,11 +1,16 @@
 // sparc_b200.cu -- sm_100a kernels + the C ABI of include/sparc_b200.h.
 //
-// One fused kernel per env step: a CTA owns a tile of consecutive envs; the first threads run
-// the dynamics (one env per thread: legality, move / traceback undo, trie-cursor reward,
-// truncation, terminal rule validation, statistics, autoreset), then the whole CTA expands the
-// tile's bit-packed planes into the caller's int32/int64 observation tensors with coalesced
-// 16-byte streaming stores.  The kernel is HBM-write bound: per env-step it
-// writes X*Y*(4P+4+8) observation bytes and touches ~100 bytes of state.
+// One env step of a big batch (>= 8,192 envs) is three launches:
+//   k_dyn     one env per thread: legality, move / traceback undo, trie-cursor reward, truncation,
+//             statistics, autoreset; terminal states are queued as 48-byte snapshots
+//   k_val     walks that queue (rule validation: flood fill, colour rules, exact polyomino fit) on a side
+//             stream, beside ...
+//   k_encode  state -> observation: a CTA owns a tile of 8 consecutive envs, stages their bit-packed planes
+//             in shared memory and expands them into the caller's int32/int64 tensors with coalesced
+//             16-byte streaming stores.  HBM-write bound: X*Y*(4P+4+8) bytes per env-step.
+// Small batches use the fused k_env (one launch, one tile per CTA).  k_env_ring is an opt-in persistent,
+// warp-specialised variant (mbarrier hand-off, optional TMA bulk stores) kept for experiments.
+// The device functions themselves (dynamics, validator, encoder) live in sparc_core.cuh.
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <string.h>
