@@ -59,35 +59,60 @@ def ncu_traffic(workload, n_env):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock and throttle reasons of one GPU while it is under load: NVML in-process (pynvml), or the
+    nvidia-smi query of B200_PROFILING.md when pynvml is missing."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, index):
+    def __init__(self, index, period=0.05):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+        self.index, self.period, self.rows, self.stop_flag = index, period, [], threading.Event()
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # LOCAL_RANK counts visible devices: honour CUDA_VISIBLE_DEVICES
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nvml = None
+
+    def _sample(self):
+        if self.nvml is not None:
+            n = self.nvml
+            mhz = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+            r = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") \
+                else n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+            bits = [0x8, 0x40, 0x20, 0x4]     # HwSlowdown, HwThermalSlowdown, SwThermalSlowdown, SwPowerCap
+            return [str(mhz), str(self.max_mhz)] + ["Active" if r & b else "Not Active" for b in bits]
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        return [c.strip() for c in out.split(",")] if out else None
 
     def run(self):
         while not self.stop_flag.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                row = self._sample()
+                if row:
+                    self.rows.append(row)
             except Exception:
                 pass
-            self.stop_flag.wait(0.1)
+            self.stop_flag.wait(self.period if self.nvml is not None else 0.2)
 
     def summary(self):
         self.stop_flag.set()
         self.join(timeout=6)
         if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock samples (neither NVML nor nvidia-smi)"]}
         sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for k, n in enumerate(names) if any(r[2 + k].lower() == "active" for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
-                "reasons": reasons, "samples": len(self.rows)}
+        reasons = [n for k, n in enumerate(self.NAMES) if any(r[2 + k].lower() == "active" for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_min_mhz": sm[0] if sm else None,
+                "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.rows), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -243,7 +268,11 @@ def main():
     ms = ev0.elapsed_time(ev1)
     launches = env.kernel_launches - launches0          # the ABI counts at capture time too: kernel nodes of the graph
     t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    per_rank_ms = [ms]
     if world > 1:
+        gathered = [torch.zeros_like(t_ms) for _ in range(world)]
+        dist.all_gather(gathered, t_ms)
+        per_rank_ms = [float(g.item()) for g in gathered]
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     ms_max = float(t_ms.item())
 
@@ -326,7 +355,8 @@ def main():
                        "l2": ("observation written per step (%.0f MB) exceeds L2 (126 MB)" % (b_alg * n_env / 1e6))
                              if b_alg * n_env > 126e6 else
                              ("observation per step (%.1f MB) fits in L2: writes may be absorbed by L2" % (b_alg * n_env / 1e6)),
-                       "parallelism": f"env-sharded x{world}, no data-path collective", "setup_s": round(t_build, 1)},
+                       "parallelism": f"env-sharded x{world}, no data-path collective", "setup_s": round(t_build, 1),
+                       "ms_per_step_by_rank": [round(m / K, 5) for m in per_rank_ms]},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": ncu_traffic(args.workload, n_env), "peak_source": peak_src,
