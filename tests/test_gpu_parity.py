@@ -125,3 +125,29 @@ def test_step_host_matches_device_step():
             ob, rb, tb, ub, _ = b.step(act.cuda())
             assert torch.equal(r, rb.cpu()) and torch.equal(te, tb.cpu()) and torch.equal(tr, ub.cpu()), (n, t)
             assert all(torch.equal(a.obs[k], ob[k]) for k in ob)
+
+
+def test_long_episodes_hit_max_steps_like_the_emulation():
+    """1,100 steps with max_steps=1000 and traceback: deep move stacks, the `current_step >= max_steps`
+    truncation (SG.py:1134) and the cyclic puzzle cursor wrapping around the pool, GPU vs the CPU build."""
+    from emu.emu_env import EmuVecEnv
+    rows = gen_pool(7, [(3, 3), (4, 4), (6, 6)], RULES_FULL, seed0=900)
+    N, T = 1024, 1100
+    kw = dict(traceback=True, max_steps=1000, autoreset_mode="next_step", validate="terminal", puzzle_stride=5)
+    g, c = make_env(rows, N, **kw), EmuVecEnv(rows, N, tile=32, **kw)
+    g.reset(); c.reset()
+    rng = np.random.default_rng(11)
+    hit_max = 0
+    for t in range(T):
+        a = rng.integers(0, 4, N).astype(np.uint8)
+        go, gr, gt, gu, gi = g.step(torch.from_numpy(a).cuda())
+        co, cr, ct, cu, ci = c.step(a)
+        if t % 50 == 0 or t > 990:
+            for k in go:
+                assert np.array_equal(to_np(go[k]), co[k]), (t, k)
+        assert np.array_equal(to_np(gi["reward_code"]), ci["reward_code"]), t
+        assert np.array_equal(to_np(gt), ct) and np.array_equal(to_np(gu), cu), t
+        assert np.array_equal(to_np(gi["current_step"]), ci["current_step"]), t
+        hit_max += int(((ci["current_step"] >= 1000) & (cu == 1)).sum())
+    assert hit_max > 0, "no env survived to max_steps: the truncation path was not exercised"
+    assert np.array_equal(to_np(g.stats()), c.stats())
