@@ -118,8 +118,6 @@ struct StepCfg {
 
 struct StepResult {
     int reward_code, terminated, truncated, legal_mask, rule_flags;
-    int stat_done, stat_stepped;   // for the statistics reduction
-    int final_step, final_ret, final_win;
 };
 
 SPARC_HD uint32_t board_word(const uint32_t (&b)[8], int k) {
