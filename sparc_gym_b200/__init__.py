@@ -4,7 +4,7 @@ The hot path of tobiTKM/SPaRC-Gym (reset -> step -> terminal rule validation -> 
 observation) as hand-written sm_100a CUDA behind a C ABI (include/sparc_b200.h), with the
 reference's Gymnasium surface on top:
 
-    SparcVecEnv      N lockstep envs on one GPU (vec_env.py)
+    SparcVecEnv      N lockstep envs on one GPU; SparcVectorEnv = its gymnasium.vector-shaped face (vec_env.py)
     ShardedRunner    env-sharded multi-GPU runner, NCCL all-reduce of episode statistics (runner.py)
     SPaRC_Gym        single-env drop-in for gym.make('SPaRC-Gym' | 'SPaRc-Gym') (gym_env.py)
 

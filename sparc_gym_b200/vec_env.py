@@ -214,3 +214,45 @@ class SparcVecEnv:
             self.close()
         except Exception:
             pass
+
+
+class SparcVectorEnv(SparcVecEnv):
+    """`gymnasium.vector.VectorEnv`-shaped face of SparcVecEnv (duck-typed: gymnasium is optional).
+
+    `reset(seed=None, options=None) -> (obs, info)`, `step(actions) -> (obs, reward, terminated,
+    truncated, info)` with batched CUDA tensors; `options={'puzzle_id': [...]}` or
+    `{'puzzle_index': tensor}` picks puzzles like the reference's `reset(options=...)`
+    (SG.py:1076-1082); a seed draws the per-env puzzle indices from `np.random.default_rng(seed)`
+    (the reference draws one index for its one env, SG.py:1084-1085).  `info` carries
+    `legal_mask` (bit a = action a legal; callers of the reference gate on
+    `info["legal_actions"]`, human_play.py:55), `rule_flags`, `current_step`, `agent_location`.
+    """
+
+    metadata = {"autoreset_mode": None}
+
+    def __init__(self, puzzles, num_envs, **kwargs):
+        super().__init__(puzzles, num_envs, **kwargs)
+        from .gym_env import _spaces
+        st = self.store
+        self.metadata = {"autoreset_mode": self.autoreset_mode}
+        self.single_action_space = _spaces.Discrete(4)
+        self.single_observation_space = _spaces.Dict({
+            "base": _spaces.Box(low=0, high=1, shape=(st.n_planes, st.slab_x, st.slab_y), dtype=np.int32),
+            "color": _spaces.Box(low=0, high=8, shape=(st.slab_x, st.slab_y), dtype=np.int32),
+            "additional_info": _spaces.Box(low=0, high=143632, shape=(st.slab_x, st.slab_y), dtype=np.int64)})
+        self.action_space, self.observation_space = self.single_action_space, self.single_observation_space
+        self.plane_keys = list(st.plane_keys)
+
+    def reset(self, *, seed=None, options=None, mask=None):
+        idx = None
+        if options:
+            if "puzzle_index" in options:
+                idx = options["puzzle_index"]
+            elif "puzzle_id" in options:
+                ids = options["puzzle_id"]
+                ids = [ids] * self.num_envs if isinstance(ids, str) else list(ids)
+                cur = torch.arange(self.num_envs) % self.store.n_puzzles
+                idx = torch.tensor([self.store.id_to_index.get(i, int(c)) for i, c in zip(ids, cur)], dtype=torch.int32)
+        elif seed is not None:
+            idx = torch.from_numpy(np.random.default_rng(seed).integers(self.store.n_puzzles, size=self.num_envs).astype(np.int32))
+        return super().reset(puzzle_idx=idx, mask=mask)

@@ -151,3 +151,20 @@ def test_long_episodes_hit_max_steps_like_the_emulation():
         hit_max += int(((ci["current_step"] >= 1000) & (cu == 1)).sum())
     assert hit_max > 0, "no env survived to max_steps: the truncation path was not exercised"
     assert np.array_equal(to_np(g.stats()), c.stats())
+
+
+def test_vector_env_face_reset_options():
+    from sparc_gym_b200.vec_env import SparcVectorEnv
+    rows = gen_pool(6, [(3, 3), (4, 4)], RULES_FULL, seed0=40)
+    env = SparcVectorEnv(rows, 12, max_steps=20, autoreset_mode="next_step")
+    obs, info = env.reset(options={"puzzle_id": rows[4]["id"]})
+    one = {k: v[0].clone() for k, v in obs.items()}
+    assert all(torch.equal(v[i], one[k]) for k, v in obs.items() for i in range(12))       # every env on puzzle 4
+    obs, info = env.reset(seed=3)
+    want = np.random.default_rng(3).integers(6, size=12)
+    solo = SparcVectorEnv(rows, 12, max_steps=20)
+    o2, _ = solo.reset(options={"puzzle_index": torch.tensor(want, dtype=torch.int32)})
+    assert all(torch.equal(obs[k], o2[k]) for k in obs)
+    assert env.single_observation_space is not None and env.num_envs == 12 and env.plane_keys[:4] == ["visited", "gaps", "agent_location", "target_location"]
+    out = env.step(torch.zeros(12, dtype=torch.int64, device="cuda"))
+    assert len(out) == 5 and out[1].shape == (12,)
