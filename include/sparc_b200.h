@@ -37,6 +37,12 @@ extern "C" {
 #define SPARC_MAX_PLANES     10      /* visited,gaps,agent_location,target_location + 6 symbol kinds */
 #define SPARC_MAX_SHAPES     32      /* distinct polyshapes referenced by one puzzle */
 #define SPARC_MAX_YLOPS       6      /* ylop instances in one puzzle (3-bit demand counters) */
+#define SPARC_MAX_REGIONS    64      /* region ids per env (one per rule cell at most: 7 x 7 = 49) */
+/* poly/ylop verdict of one region (SG.py:674-702) */
+enum { SPARC_FIT_NONE = 0,           /* no poly / ylop instance in the region */
+       SPARC_FIT_AREA_MISMATCH = 1,  /* sum(poly) - sum(ylop) != region area: exact fit skipped */
+       SPARC_FIT_NO_TILING = 2,      /* area matches, no exact placement exists */
+       SPARC_FIT_OK = 3 };
 
 /* error codes */
 #define SPARC_OK              0
@@ -200,9 +206,10 @@ int sparc_encode(SparcEnv* env, const SparcObsOut* obs, void* stream);
 
 /* replaces _validate_rules() (SG.py:941-950) on the current state of the masked envs (NULL = all).
  * flags_dev: uint16[n_envs]; region_map_dev: int8[n_envs][slab_x][slab_y] (-1 off-cell,
- * SG.py:429-454) or NULL. */
+ * SG.py:429-454) or NULL; region_fit_dev: int8[n_envs][SPARC_MAX_REGIONS] or NULL -- the poly/ylop
+ * verdict SPARC_FIT_* of every region id (the `region_details` of SG.py:674-702). */
 int sparc_validate(SparcEnv* env, const uint8_t* mask_dev, uint16_t* flags_dev,
-                   int8_t* region_map_dev, void* stream);
+                   int8_t* region_map_dev, int8_t* region_fit_dev, void* stream);
 
 /* episode statistics accumulated since creation / the last clear: copies int64[SPARC_N_STATS]
  * to out_dev (device) on `stream`; clear != 0 zeroes the accumulators afterwards. */

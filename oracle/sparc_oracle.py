@@ -257,24 +257,46 @@ def validate(pz, path, agent, target, *, reference_cost=False):
             c = int(color[x, y])
             if c:
                 colors[rid][c] = colors[rid].get(c, 0) + 1
-    flags = {}
+    flags, det = {}, {}
     flags["reached_target"] = bool(agent[0] == target[0] and agent[1] == target[1])    # SG.py:488
+    det["reached_target"] = {"agent_loc": [int(v) for v in agent], "target_loc": [int(v) for v in target]}
     pt = [tuple(p) for p in path]
-    flags["path_not_crossing"] = len(set(pt)) == len(pt)                               # SG.py:498
-    flags["no_gap_violations"] = all(planes["gaps"][x, y] != 1 for x, y in pt)         # SG.py:508
+    dup = {}                                                                           # SG.py:498
+    for q in pt:
+        dup[q] = dup.get(q, 0) + 1
+    dup = {k: v for k, v in dup.items() if v > 1}
+    flags["path_not_crossing"] = len(dup) == 0
+    det["path_not_crossing"] = {"duplicates": dup}
+    viol = [(x, y) for x, y in pt if planes["gaps"][x, y] == 1]                        # SG.py:508
+    flags["no_gap_violations"] = len(viol) == 0
+    det["no_gap_violations"] = {"violations": viol}
     if "dot" in planes:                                                                # SG.py:521
         d = planes["dot"] == 1
-        flags["all_dots_collected"] = int((d & (planes["visited"] == 1)).sum()) == int(d.sum())
+        total, got = int(d.sum()), int((d & (planes["visited"] == 1)).sum())
+        flags["all_dots_collected"] = got == total
+        det["all_dots_collected"] = {"total": total, "collected": got}
     else:
         flags["all_dots_collected"] = True
+        det["all_dots_collected"] = {"total": 0, "collected": 0}
     ok = True                                                                          # SG.py:534
     if "square" in planes:
+        bad, rows = [], []
         for r in range(len(regions)):
-            cs = {int(color[x, y]) for x, y in sym[r].get("square", []) if color[x, y] != 0}
-            ok &= len(cs) <= 1
+            squares = sym[r].get("square", [])
+            if not squares:
+                continue
+            cs = set(color[x, y] for x, y in squares if color[x, y] != 0)   # numpy scalars, like SG.py:547
+            if len(cs) > 1:
+                bad.append(r)
+            rows.append({"region": r, "square_count": len(squares), "colors": list(cs)})
+        ok = not bad
+        det["square_color_separation"] = {"violating_regions": bad, "region_square_details": rows}
+    else:
+        det["square_color_separation"] = {"regions": []}
     flags["square_color_separation"] = ok
     ok = True                                                                          # SG.py:554
     if "star" in planes:
+        violations, per_region = [], []
         for r in range(len(regions)):
             stars = sym[r].get("star", [])
             if not stars:
@@ -282,15 +304,30 @@ def validate(pz, path, agent, target, *, reference_cost=False):
             total = {}
             for coords in sym[r].values():
                 for x, y in coords:
-                    c = int(color[x, y])
-                    if c:
+                    c = color[x, y]
+                    if c != 0:
                         total[c] = total.get(c, 0) + 1
+            star_colors = {}
             for x, y in stars:
-                c = int(color[x, y])
-                if c == 0 or total.get(c, 0) != 2:
-                    ok = False
+                c = color[x, y]
+                if c == 0:
+                    violations.append({"region": r, "color": 0, "found_total": 1})
+                    continue
+                star_colors[c] = star_colors.get(c, 0) + 1
+            region_ok, rows = True, []
+            for c, n_star in star_colors.items():
+                tc = total.get(c, 0)
+                if tc != 2:
+                    region_ok = False
+                    violations.append({"region": r, "color": c, "found_total": tc, "star_cells": n_star})
+                rows.append({"color": c, "total_symbols_of_color": tc, "star_cells": n_star, "ok": tc == 2})
+            per_region.append({"region": r, "details": rows, "all_ok": region_ok})
+        ok = not violations
+        det["star_pairing_exact"] = {"violations": violations, "per_region": per_region}
+    else:
+        det["star_pairing_exact"] = {"regions": []}
     flags["star_pairing_exact"] = ok
-    ok = True                                                                          # SG.py:617
+    mism = []                                                                          # SG.py:617
     if "triangle" in planes:
         tri = planes["triangle"]
         pset = set(pt)
@@ -298,38 +335,57 @@ def validate(pz, path, agent, target, *, reference_cost=False):
             for y in range(1, Y - 1):
                 if tri[x, y] == 1 and int(info[x, y]) > 0:
                     t = sum(((x + dx, y + dy) in pset) for dx, dy in DIRECTIONS)
-                    ok &= t == int(info[x, y])
-    flags["triangles_edge_count"] = ok
+                    if t != int(info[x, y]):
+                        mism.append({"x": x, "y": y, "required": int(info[x, y]), "touches": t})
+    flags["triangles_edge_count"] = not mism
+    det["triangles_edge_count"] = {"mismatches": mism}
     # poly / ylop (SG.py:648-736)
     ok = True
     shapes = pz["polyshapes"]
+    det["poly_ylop_area"] = {"regions": []}
     if isinstance(shapes, dict):
-        by_region = {}
+        by_region, any_inst = {}, False
         for x in range(X):
             for y in range(Y):
                 v = info[x, y]
                 if v != 0 and f"{v}" in shapes:
                     kind = "poly" if planes["poly"][x, y] == 1 else "ylop"  # KeyError as in SG.py:734
+                    any_inst = True
                     rid = region_map[x, y]
                     if rid != -1:
                         by_region.setdefault(int(rid), []).append((f"{v}", kind))
-        if by_region and reference_cost:
+        if any_inst and reference_cost:
             compute_regions(planes, path)   # the reference recomputes the regions here (SG.py:660)
+        rows = []
         for rid, insts in by_region.items():
             area = {n: int(np.array(shapes[n]).sum()) for n, _ in insts}
-            net = sum(area[n] for n, k in insts if k == "poly") - sum(area[n] for n, k in insts if k == "ylop")
-            if net != len(regions[rid]):
-                ok = False
-                continue
-            polys = [(n, shapes[n]) for n, k in insts if k == "poly"]
-            ylops = [(n, shapes[n]) for n, k in insts if k == "ylop"]
-            ok &= exact_fit(X, Y, regions[rid], polys, ylops)
+            pa = sum(area[n] for n, k in insts if k == "poly")
+            ya = sum(area[n] for n, k in insts if k == "ylop")
+            net, ra = pa - ya, len(regions[rid])
+            row = {"region": rid, "area_check": {"region_area": ra, "poly_area": pa, "ylop_area": ya,
+                                                 "net": net, "ok": ra == net}}
+            if net != ra:
+                fit = False
+                row["exact_fit"] = {"ok": False, "skipped": True}
+            else:
+                polys = [(n, shapes[n]) for n, k in insts if k == "poly"]
+                ylops = [(n, shapes[n]) for n, k in insts if k == "ylop"]
+                fit = exact_fit(X, Y, regions[rid], polys, ylops)
+                row["exact_fit"] = {"ok": fit, "region_id": rid, "region_area": ra, "poly_area": pa,
+                                    "ylop_area": ya, "net": net}
+            row["ok"] = fit
+            ok &= fit
+            rows.append(row)
+        if any_inst:
+            det["poly_ylop_area"] = {"violations": [r["region"] for r in rows if not r["ok"]],
+                                     "region_details": rows}
     flags["poly_ylop_area"] = ok
     flags["all_rules_satisfied"] = all(flags[k] for k in RULE_NAMES[:8])               # SG.py:932-935
+    det["all_rules_satisfied"] = {"rules_checked": list(RULE_NAMES[:8])}
     summaries = {r: {"id": r, "area": len(regions[r]),
                      "symbol_counts": {k: len(v) for k, v in sym[r].items()},
                      "colors": colors[r]} for r in range(len(regions))}
-    return flags, summaries, region_map
+    return flags, summaries, region_map, det
 
 
 # --------------------------------------------------------------------------------------
@@ -416,9 +472,9 @@ class OracleEnv:
         return json.dumps(self.observ, separators=(",", ":"))               # SG.py:992
 
     def _info(self):
-        flags, regions, _ = validate(self.pz, self.path, self.agent, self.target,
-                                     reference_cost=self.reference_cost)    # SG.py:1011
-        status = {k: {"passed": bool(v)} for k, v in flags.items()}
+        flags, regions, _, det = validate(self.pz, self.path, self.agent, self.target,
+                                          reference_cost=self.reference_cost)    # SG.py:1011
+        status = {k: {"passed": bool(v), "detail": det[k]} for k, v in flags.items()}
         status["_terminated"] = {"passed": True, "detail": False}           # Q16
         status["_truncated"] = {"passed": True, "detail": False}
         status["_regions"] = regions

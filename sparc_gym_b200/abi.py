@@ -24,6 +24,8 @@ MAX_PLANES = 10
 N_STATS = 8
 STAT_NAMES = ("episodes", "solved", "failed", "truncated", "steps", "return_cents", "length", "rules_pass")
 RULE_VALID = 1 << 15
+MAX_REGIONS = 64                              # SPARC_MAX_REGIONS
+FIT_NONE, FIT_AREA_MISMATCH, FIT_NO_TILING, FIT_OK = 0, 1, 2, 3   # SPARC_FIT_*: per-region poly/ylop verdicts
 AUTORESET = {"disabled": 0, "next_step": 1, "same_step": 2}
 VALIDATE = {"never": 0, "terminal": 1, "every_step": 2}
 ACT_DTYPES = {"uint8": 0, "int32": 1, "int64": 2}
@@ -100,7 +102,7 @@ def load_library():
     lib.sparc_reset.argtypes = [vp, vp, vp, C.POINTER(StepOut), C.POINTER(ObsOut), vp]
     lib.sparc_step.argtypes = [vp, vp, i32, C.POINTER(StepOut), C.POINTER(ObsOut), vp]
     lib.sparc_encode.argtypes = [vp, C.POINTER(ObsOut), vp]
-    lib.sparc_validate.argtypes = [vp, vp, vp, vp, vp]
+    lib.sparc_validate.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.sparc_stats.argtypes = [vp, vp, i32, vp]
     lib.sparc_step_host.argtypes = [vp, vp, vp, vp, vp, C.POINTER(ObsOut), vp]
     lib.sparc_state_bytes.argtypes = [vp]

@@ -117,6 +117,11 @@ __global__ void __launch_bounds__(CTA_THREADS, SPARC_MINBLOCKS) k_env(const KPar
 #endif
 // INLINE_VALIDATION = false: terminal states are only queued (k_val validates them), which drops the
 // validator from this kernel's register budget (145 -> ~60) and doubles its resident warps.
+// (Programmatic dependent launch of k_encode behind k_dyn -- griddepcontrol.launch_dependents at the top of k_dyn,
+// griddepcontrol.wait in k_encode after a speculative prefetch of the puzzle's encoder inputs -- was measured inside
+// the CUDA graph of bench.py: 0.196 -> 0.202 ms/step at 131,072 envs, 0.108 -> 0.117 at 65,536, 0.044 -> 0.051 at
+// 16,384.  The parked encoder CTAs take registers and issue slots from the latency-bound dynamics; the graph's
+// kernel-to-kernel edge is already ~1 us.  Removed.)
 template <bool INLINE_VALIDATION>
 __global__ void __launch_bounds__(CTA_THREADS, DYN_MINBLOCKS) k_dyn(const KParams p, long long lo, long long hi) {
     const long long i = lo + (long long)blockIdx.x * CTA_THREADS + threadIdx.x;
@@ -410,9 +415,12 @@ __global__ void __launch_bounds__(RING_THREADS, 1) k_env_ring(const KParams p, u
 
 // stand-alone validator (SG.py:941-950) for sparc_validate: one env per thread
 __global__ void __launch_bounds__(CTA_THREADS) k_validate(const StoreDev st, const StateDev sd, long long n,
-                                                          const uint8_t* mask, uint16_t* flags, int8_t* region_map) {
+                                                          const uint8_t* mask, uint16_t* flags, int8_t* region_map,
+                                                          int8_t* region_fit) {
     const long long i = (long long)blockIdx.x * CTA_THREADS + threadIdx.x;
     if (i >= n) return;
+    int8_t* rf = region_fit ? region_fit + (size_t)i * SPARC_MAX_REGIONS : nullptr;
+    if (rf) for (int k = 0; k < SPARC_MAX_REGIONS; k++) rf[k] = SPARC_FIT_NONE;
     if (mask && !mask[i]) { if (flags) flags[i] = 0; return; }
     EnvRegs e;
     load_env(e, sd, st, n, i);
@@ -422,7 +430,7 @@ __global__ void __launch_bounds__(CTA_THREADS) k_validate(const StoreDev st, con
     vd[8] = 0;
     int8_t* rm = region_map ? region_map + (size_t)i * st.S : nullptr;
     if (rm) for (int k = 0; k < st.S; k++) rm[k] = -1;
-    const int f = validate_env(st, e.puzzle, vd, e.x, e.y, rm);
+    const int f = validate_env(st, e.puzzle, vd, e.x, e.y, rm, rf);
     if (flags) flags[i] = (uint16_t)(f | SPARC_RULE_VALID);
 }
 
@@ -560,6 +568,8 @@ int sparc_env_create(SparcStore* store, int64_t n_envs, int traceback, int max_s
                 cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, store->device);
                 (void)dev_sms;
                 e->val_grid = 32;              // x128 threads; a small grid disturbs the co-running encoder least (measured)
+                const char* ve = getenv("SPARC_VAL_GRID");
+                if (ve && atoi(ve) > 0) e->val_grid = atoi(ve);
             }
             if (se != cudaSuccess) { delete e; return fail(SPARC_E_CUDA, "side stream / queue: %s", cudaGetErrorString(se)); }
             e->split_chunks = nc;
@@ -647,28 +657,27 @@ static int launch_env(SparcEnv* e, KParams& p, void* stream) {
                 CU(cudaEventRecord(e->ev_dyn[c], e->side));
                 CU(cudaStreamWaitEvent(s0, e->ev_dyn[c], 0));
             }
-            if (e->hostcopy.active && nc == 1) {                             // fork: results -> host beside k_encode
+            const bool last = hi >= n;
+            const bool fork_val = defer && last;
+            const bool fork_copy = e->hostcopy.active && nc == 1;
+            if (nc == 1 && (fork_val || fork_copy)) CU(cudaEventRecord(e->ev_start, s0));   // = k_dyn done
+            if (any_obs) k_encode<<<(unsigned)((hi - lo + p.tile - 1) / p.tile), ENC_THREADS, shmem, s0>>>(p, lo, hi);
+            if (fork_copy) {                                                 // results -> host beside k_encode
                 const size_t nn = (size_t)n;
-                CU(cudaEventRecord(e->ev_dyn_done, s0));
-                CU(cudaStreamWaitEvent(e->copy_stream, e->ev_dyn_done, 0));
+                CU(cudaStreamWaitEvent(e->copy_stream, e->ev_start, 0));
                 if (e->hostcopy.reward) CU(cudaMemcpyAsync(e->hostcopy.reward, e->rew_stage, nn * 4, cudaMemcpyDeviceToHost, e->copy_stream));
                 if (e->hostcopy.term) CU(cudaMemcpyAsync(e->hostcopy.term, e->term_stage, nn, cudaMemcpyDeviceToHost, e->copy_stream));
                 if (e->hostcopy.trunc) CU(cudaMemcpyAsync(e->hostcopy.trunc, e->trunc_stage, nn, cudaMemcpyDeviceToHost, e->copy_stream));
                 CU(cudaEventRecord(e->ev_copy, e->copy_stream));
             }
-            const bool last = hi >= n;
-            if (defer && last) {                                             // fork: k_val beside (the last) k_encode
-                if (nc == 1) {
-                    CU(cudaEventRecord(e->ev_start, s0));
-                    CU(cudaStreamWaitEvent(e->side, e->ev_start, 0));
-                }
+            if (fork_val) {                                                  // k_val beside (the last) k_encode
+                if (nc == 1) CU(cudaStreamWaitEvent(e->side, e->ev_start, 0));
                 k_val<<<(unsigned)e->val_grid, CTA_THREADS, 0, e->side>>>(p);
                 CU(cudaEventRecord(e->ev_val, e->side));
                 e->launches++;
+                CU(cudaStreamWaitEvent(s0, e->ev_val, 0));                   // join
             }
-            if (any_obs) k_encode<<<(unsigned)((hi - lo + p.tile - 1) / p.tile), ENC_THREADS, shmem, s0>>>(p, lo, hi);
-            if (defer && last) CU(cudaStreamWaitEvent(s0, e->ev_val, 0));    // join
-            if (e->hostcopy.active && nc == 1) CU(cudaStreamWaitEvent(s0, e->ev_copy, 0));
+            if (fork_copy) CU(cudaStreamWaitEvent(s0, e->ev_copy, 0));
             e->launches += any_obs ? 2 : 1;
         }
         CU(cudaGetLastError());
@@ -720,11 +729,12 @@ int sparc_encode(SparcEnv* e, const SparcObsOut* obs, void* stream) {
     return SPARC_OK;
 }
 
-int sparc_validate(SparcEnv* e, const uint8_t* mask_dev, uint16_t* flags_dev, int8_t* region_map_dev, void* stream) {
+int sparc_validate(SparcEnv* e, const uint8_t* mask_dev, uint16_t* flags_dev, int8_t* region_map_dev,
+                   int8_t* region_fit_dev, void* stream) {
     if (!e) return fail(SPARC_E_ARG, "null env%s");
     const int64_t n = e->cfg.n_envs;
     k_validate<<<(unsigned)((n + CTA_THREADS - 1) / CTA_THREADS), CTA_THREADS, 0, (cudaStream_t)stream>>>(
-        e->store->d, e->s, n, mask_dev, flags_dev, region_map_dev);
+        e->store->d, e->s, n, mask_dev, flags_dev, region_map_dev, region_fit_dev);
     CU(cudaGetLastError());
     e->launches++;
     return SPARC_OK;

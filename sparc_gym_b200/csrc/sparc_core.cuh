@@ -496,8 +496,11 @@ SPARC_HD bool exact_fit(uint64_t region, int w, int h, const SparcShape* shapes,
 
 // vd: the env's visited plane in dense slab order, 9 readable words (word 8 may be anything
 // when S <= 256).  region_map: optional int8[SX*SY] (row-major x, y), pre-filled with -1.
+// region_fit: optional int8[SPARC_MAX_REGIONS], pre-filled with SPARC_FIT_NONE: the poly/ylop verdict of every
+// region (SG.py:674-702); asking for it makes the poly rule look at every region instead of stopping at the
+// first failure.
 SPARC_HD int validate_env(const StoreDev& st, uint32_t puzzle, const uint32_t* vd, int ax, int ay,
-                          int8_t* region_map) {
+                          int8_t* region_map, int8_t* region_fit = nullptr) {
     const HdrRegs h = load_hdr(st, puzzle);
     const uint32_t* nbp = st.nb + (size_t)puzzle * SPARC_N_NODE_BOARDS * 8;
     // visited: dense -> 16-stride
@@ -549,7 +552,7 @@ SPARC_HD int validate_env(const StoreDev& st, uint32_t puzzle, const uint32_t* v
     // regions (SG.py:422-454): passable = rule cell, or neither gap nor path (Q6).  The three
     // region rules are vacuously true for a puzzle without stars, squares and shape instances,
     // so its region pass is skipped unless the caller wants the region map itself.
-    if (!(h.flags & 2) && !region_map) {
+    if (!(h.flags & 2) && !region_map && !region_fit) {
         flags |= SPARC_RULE_SQUARES | SPARC_RULE_STARS | SPARC_RULE_POLY_YLOP;
         if ((flags & 0xFF) == 0xFF) flags |= SPARC_RULE_ALL;
         return flags;
@@ -625,7 +628,7 @@ SPARC_HD int validate_env(const StoreDev& st, uint32_t puzzle, const uint32_t* v
             }
         }
         // polys / ylops (SG.py:648-710)
-        if (h.n_shapes && poly_ok) {
+        if (h.n_shapes && (poly_ok || region_fit)) {
             uint8_t np[SPARC_MAX_SHAPES], nyl[SPARC_MAX_SHAPES];
             int net = 0, any = 0;
             for (int s = 0; s < h.n_shapes; s++) {
@@ -634,8 +637,11 @@ SPARC_HD int validate_env(const StoreDev& st, uint32_t puzzle, const uint32_t* v
                 net += (a - b) * (int)shapes[s].area;
             }
             if (any) {
-                if (net != sp_popcll(R)) poly_ok = false;   // SG.py:679-682
-                else if (!exact_fit(R, w, hh, shapes, h.n_shapes, np, nyl)) poly_ok = false;
+                int verdict = SPARC_FIT_OK;
+                if (net != sp_popcll(R)) verdict = SPARC_FIT_AREA_MISMATCH;   // SG.py:679-682
+                else if (!exact_fit(R, w, hh, shapes, h.n_shapes, np, nyl)) verdict = SPARC_FIT_NO_TILING;
+                if (verdict != SPARC_FIT_OK) poly_ok = false;
+                if (region_fit && rid < SPARC_MAX_REGIONS) region_fit[rid] = (int8_t)verdict;
             }
         }
         rid++;

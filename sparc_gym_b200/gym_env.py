@@ -10,9 +10,11 @@ int64[X, Y]}` and the arrays are owned by the env and updated in place (SG.py:97
 
 All dynamics, rewards, rule validation and the observation planes come from the CUDA library
 (one env on the GPU); this class only converts device arrays into the reference's containers.
-Deliberate differences: resets are clean, `info['rule_status'][rule]['detail']` is
-reduced to what the device computes, and there are no pygame renderers.  observation='SPaRC'
-(the JSON text grid, SG.py:1149-1184) is assembled on the host from the device's dynamics.
+`info['rule_status'][rule]['detail']` (SG.py:488-710) is assembled on the host from what the
+device returns: the rule flags, the region map and the per-region poly/ylop verdicts.
+Deliberate differences: resets are clean and there are no pygame renderers.
+observation='SPaRC' (the JSON text grid, SG.py:1149-1184) is assembled on the host from the
+device's dynamics.
 """
 from __future__ import annotations
 
@@ -122,7 +124,7 @@ class SPaRC_Gym(_Env):
     def _pull(self):
         """Copy the device results of the last reset/step into the reference's containers."""
         v, st, pz = self._vec, self._store, self._pz
-        flags, rmap = v.validate(region_map=True)
+        flags, rmap, rfit = v.validate(region_map=True, region_fit=True)
         base = v.obs["base"][0].cpu().numpy()
         for pi, key in enumerate(st.plane_keys):
             if key in self.obs_array:
@@ -135,12 +137,16 @@ class SPaRC_Gym(_Env):
         f = int(flags[0]) & 0xFFFF
         self._flags = {name: bool((f >> k) & 1) for k, name in enumerate(RULE_NAMES)}
         self._region_map = rmap[0, :pz.X, :pz.Y].cpu().numpy()
+        self._region_fit = rfit[0].cpu().numpy()
 
-    def _regions_summary(self):
-        """`_regions` of SG.py:949 from the device's region map + the puzzle's planes (SG.py:456-482)."""
+    def _region_symbols(self):
+        """Per region id: area, symbols[layer] = [(x, y), ...] and colour counts (SG.py:456-482), from the
+        device's region map and the puzzle's planes."""
         rmap = self._region_map
         n = int(rmap.max()) + 1
-        out = {r: {"id": r, "area": int((rmap == r).sum()), "symbol_counts": {}, "colors": {}} for r in range(n)}
+        area = [int((rmap == r).sum()) for r in range(n)]
+        symbols = [dict() for _ in range(n)]
+        colors = [dict() for _ in range(n)]
         for layer, arr in self.obs_array.items():
             if layer in FIXED_KEYS:
                 continue
@@ -148,12 +154,121 @@ class SPaRC_Gym(_Env):
                 rid = int(rmap[x, y])
                 if rid == -1:
                     continue
-                sc = out[rid]["symbol_counts"]
-                sc[layer] = sc.get(layer, 0) + 1
+                symbols[rid].setdefault(layer, []).append((int(x), int(y)))
                 c = self.color_array[x, y]
                 if c:
-                    out[rid]["colors"][c] = out[rid]["colors"].get(c, 0) + 1
-        return out
+                    colors[rid][c] = colors[rid].get(c, 0) + 1
+        return area, symbols, colors
+
+    def _rule_details(self, area, symbols):
+        """The `detail` payloads of SG.py:488-710.  Every fact comes from the device (flags, region map,
+        per-region poly/ylop verdicts, visited plane); this only arranges them in the reference's containers."""
+        planes, color, info = self.obs_array, self.color_array, self.additional_info
+        d = {}
+        d["reached_target"] = {"agent_loc": self._agent_location.tolist(),              # SG.py:493-496
+                               "target_loc": self._target_location.tolist()}
+        d["path_not_crossing"] = {"duplicates": {}}          # path nodes are distinct (clean resets, legal moves)
+        sx, sy = self.start_location                          # the only path node that can sit on a gap (SG.py:508-519)
+        d["no_gap_violations"] = {"violations": [(int(sx), int(sy))] if planes["gaps"][sx, sy] == 1 else []}
+        if "dot" in planes:                                                             # SG.py:521-532
+            dots = planes["dot"] == 1
+            d["all_dots_collected"] = {"total": int(dots.sum()),
+                                       "collected": int((dots & (planes["visited"] == 1)).sum())}
+        else:
+            d["all_dots_collected"] = {"total": 0, "collected": 0}
+        if "square" in planes:                                                          # SG.py:534-552
+            bad, det = [], []
+            for rid, sym in enumerate(symbols):
+                squares = sym.get("square", [])
+                if not squares:
+                    continue
+                cs = set(color[x, y] for (x, y) in squares if color[x, y] != 0)
+                if len(cs) > 1:
+                    bad.append(rid)
+                det.append({"region": rid, "square_count": len(squares), "colors": list(cs)})
+            d["square_color_separation"] = {"violating_regions": bad, "region_square_details": det}
+        else:
+            d["square_color_separation"] = {"regions": []}
+        if "star" in planes:                                                            # SG.py:554-614
+            violations, per_region = [], []
+            for rid, sym in enumerate(symbols):
+                stars = sym.get("star", [])
+                if not stars:
+                    continue
+                totals = {}
+                for coords in sym.values():
+                    for (x, y) in coords:
+                        c = color[x, y]
+                        if c != 0:
+                            totals[c] = totals.get(c, 0) + 1
+                star_colors = {}
+                for (x, y) in stars:
+                    c = color[x, y]
+                    if c == 0:
+                        violations.append({"region": rid, "color": 0, "found_total": 1})
+                        continue
+                    star_colors[c] = star_colors.get(c, 0) + 1
+                region_ok, rows = True, []
+                for c, n_star in star_colors.items():
+                    total_c = totals.get(c, 0)
+                    ok = total_c == 2
+                    if not ok:
+                        region_ok = False
+                        violations.append({"region": rid, "color": c, "found_total": total_c, "star_cells": n_star})
+                    rows.append({"color": c, "total_symbols_of_color": total_c, "star_cells": n_star, "ok": ok})
+                per_region.append({"region": rid, "details": rows, "all_ok": region_ok})
+            d["star_pairing_exact"] = {"violations": violations, "per_region": per_region}
+        else:
+            d["star_pairing_exact"] = {"regions": []}
+        if "triangle" in planes:                                                        # SG.py:617-646
+            tri, vis, mism = planes["triangle"], planes["visited"], []
+            for x in range(1, self.x_size - 1):
+                for y in range(1, self.y_size - 1):
+                    if tri[x, y] == 1 and int(info[x, y]) > 0:
+                        touches = int(vis[x + 1, y] + vis[x - 1, y] + vis[x, y - 1] + vis[x, y + 1])
+                        if touches != int(info[x, y]):
+                            mism.append({"x": x, "y": y, "required": int(info[x, y]), "touches": touches})
+            d["triangles_edge_count"] = {"mismatches": mism}
+        else:
+            d["triangles_edge_count"] = {"mismatches": []}
+        by_region = {}                                                                  # SG.py:648-736
+        if isinstance(self.polyshapes, dict):
+            for x in range(self.x_size):
+                for y in range(self.y_size):
+                    v = info[x, y]
+                    if v != 0 and f"{v}" in self.polyshapes:
+                        rid = int(self._region_map[x, y])
+                        if rid != -1:
+                            kind = "poly" if planes["poly"][x, y] == 1 else "ylop"
+                            by_region.setdefault(rid, []).append((kind, int(np.array(self.polyshapes[f"{v}"]).sum())))
+        if not by_region and not self._has_instances():
+            d["poly_ylop_area"] = {"regions": []}
+        else:
+            det = []
+            for rid, insts in by_region.items():
+                pa = sum(a for k, a in insts if k == "poly")
+                ya = sum(a for k, a in insts if k == "ylop")
+                net, verdict = pa - ya, int(self._region_fit[rid])
+                area_ok = area[rid] == net
+                assert area_ok == (verdict in (abi.FIT_OK, abi.FIT_NO_TILING)), "device / host area check disagree"
+                row = {"region": rid, "area_check": {"region_area": area[rid], "poly_area": pa, "ylop_area": ya,
+                                                     "net": net, "ok": area_ok}}
+                if area_ok:
+                    row["exact_fit"] = {"ok": verdict == abi.FIT_OK, "region_id": rid, "region_area": area[rid],
+                                        "poly_area": pa, "ylop_area": ya, "net": net}
+                else:
+                    row["exact_fit"] = {"ok": False, "skipped": True}
+                row["ok"] = area_ok and verdict == abi.FIT_OK
+                det.append(row)
+            d["poly_ylop_area"] = {"violations": [r["region"] for r in det if not r["ok"]], "region_details": det}
+        return d
+
+    def _has_instances(self):
+        """SG.py:716-736: is any node (on a rule cell or not) a poly / ylop instance?"""
+        if not isinstance(self.polyshapes, dict):
+            return False
+        nz = self.additional_info[self.additional_info != 0]
+        return any(f"{v}" in self.polyshapes for v in nz)
 
     def _build_json_obs(self):                                                  # SG.py:988-992
         import json
@@ -165,10 +280,17 @@ class SPaRC_Gym(_Env):
         return {"base": self.obs_array, "color": self.color_array, "additional_info": self.additional_info}
 
     def _get_info(self):                                                        # SG.py:994-1022
-        status = {k: {"passed": v, "detail": {}} for k, v in self._flags.items()}
+        area, symbols, colors = self._region_symbols()
+        details = self._rule_details(area, symbols)
+        core = list(RULE_NAMES[:8])
+        status = {k: {"passed": self._flags[k], "detail": details[k]} for k in core}
+        status["all_rules_satisfied"] = {"passed": self._flags["all_rules_satisfied"],
+                                         "detail": {"rules_checked": core}}            # SG.py:931-935
         status["_terminated"] = {"passed": True, "detail": False}              # SG.py:1011, 937-938 (Q16)
         status["_truncated"] = {"passed": True, "detail": False}
-        status["_regions"] = self._regions_summary()
+        status["_regions"] = {r: {"id": r, "area": area[r],                     # SG.py:949, 36-42
+                                  "symbol_counts": {k: len(v) for k, v in symbols[r].items()},
+                                  "colors": colors[r]} for r in range(len(area))}
         self.rule_status = status
         return {"solution_count": self.solution_count, "difficulty": self.difficulty,
                 "grid_x_size": self.x_size, "grid_y_size": self.y_size,

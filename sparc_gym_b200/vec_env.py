@@ -162,20 +162,24 @@ class SparcVecEnv:
             abi.check(self.lib.sparc_encode(self.handle, C.byref(self._obs_out), self._stream()))
         return self.obs
 
-    def validate(self, mask=None, region_map=False):
+    def validate(self, mask=None, region_map=False, region_fit=False):
         """Rule validation of the current state (SG.py:941-950): uint16 flags (as int16 bit
-        patterns) and optionally the region map int8[N, X, Y] (-1 off-cell, SG.py:429-454)."""
+        patterns), optionally the region map int8[N, X, Y] (-1 off-cell, SG.py:429-454) and the
+        per-region poly/ylop verdicts int8[N, abi.MAX_REGIONS] (abi.FIT_*; SG.py:674-702)."""
         flags = torch.zeros(self.num_envs, dtype=torch.int16, device=self.device)
         rmap = torch.empty((self.num_envs, self.store.slab_x, self.store.slab_y), dtype=torch.int8,
                            device=self.device) if region_map else None
+        rfit = torch.empty((self.num_envs, abi.MAX_REGIONS), dtype=torch.int8, device=self.device) if region_fit else None
         mask_ptr = None
         if mask is not None:
             self._vmask = torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
             mask_ptr = self._vmask.data_ptr()
         with torch.cuda.device(self.device):
             abi.check(self.lib.sparc_validate(self.handle, mask_ptr, flags.data_ptr(),
-                                              rmap.data_ptr() if region_map else None, self._stream()))
-        return (flags, rmap) if region_map else flags
+                                              rmap.data_ptr() if region_map else None,
+                                              rfit.data_ptr() if region_fit else None, self._stream()))
+        out = (flags,) + ((rmap,) if region_map else ()) + ((rfit,) if region_fit else ())
+        return out if len(out) > 1 else flags
 
     def stats(self, clear=False):
         """Episode statistics since creation / last clear, int64[8] on the device (abi.STAT_NAMES)."""

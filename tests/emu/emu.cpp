@@ -71,7 +71,7 @@ int emu_launch(const SparcStoreDesc* desc, uint32_t* core, uint32_t* vis, int32_
 }
 
 int emu_validate(const SparcStoreDesc* desc, uint32_t* core, uint32_t* vis, int32_t* ep_ret, long long n_envs,
-                 uint16_t* flags, int8_t* region_map) {
+                 uint16_t* flags, int8_t* region_map, int8_t* region_fit) {
     StoreDev st = make_store(desc);
     StateDev sd; sd.core = core; sd.vis = vis; sd.ep_ret = ep_ret; sd.moves = nullptr; sd.stats = nullptr;
     for (long long i = 0; i < n_envs; i++) {
@@ -82,7 +82,9 @@ int emu_validate(const SparcStoreDesc* desc, uint32_t* core, uint32_t* vis, int3
         vd[8] = 0;
         int8_t* rm = region_map ? region_map + (size_t)i * st.S : nullptr;
         if (rm) memset(rm, -1, st.S);
-        flags[i] = (uint16_t)(validate_env(st, e.puzzle, vd, e.x, e.y, rm) | SPARC_RULE_VALID);
+        int8_t* rf = region_fit ? region_fit + (size_t)i * SPARC_MAX_REGIONS : nullptr;
+        if (rf) memset(rf, SPARC_FIT_NONE, SPARC_MAX_REGIONS);
+        flags[i] = (uint16_t)(validate_env(st, e.puzzle, vd, e.x, e.y, rm, rf) | SPARC_RULE_VALID);
     }
     return 0;
 }

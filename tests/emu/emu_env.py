@@ -89,13 +89,15 @@ class EmuVecEnv:
         self._launch(0, actions=a, dtype=abi.ACT_DTYPES[name])
         return self.obs, self.reward, self.terminated, self.truncated, self._info()
 
-    def validate(self, mask=None, region_map=False):
+    def validate(self, mask=None, region_map=False, region_fit=False):
         flags = np.zeros(self.num_envs, np.uint16)
         rmap = np.zeros((self.num_envs, self.store.slab_x, self.store.slab_y), np.int8) if region_map else None
+        rfit = np.zeros((self.num_envs, abi.MAX_REGIONS), np.int8) if region_fit else None
         p = lambda a: C.c_void_p(a.ctypes.data) if a is not None else None
         self.lib.emu_validate(C.byref(self.desc), p(self.core), p(self.vis), p(self.ep_ret),
-                              C.c_longlong(self.num_envs), p(flags), p(rmap))
-        return (flags, rmap) if region_map else flags
+                              C.c_longlong(self.num_envs), p(flags), p(rmap), p(rfit))
+        out = (flags,) + ((rmap,) if region_map else ()) + ((rfit,) if region_fit else ())
+        return out if len(out) > 1 else flags
 
     def stats(self, clear=False):
         out = self.stats_acc.astype(np.int64)

@@ -25,6 +25,24 @@ def _reward_repr(r):
     return [type(r).__name__, float(r)]
 
 
+def _canon(v):
+    """JSON-able, type-insensitive form of a rule `detail` payload: numpy scalars -> int, tuples -> lists,
+    dict keys -> str; container order is kept (it is part of what is compared)."""
+    if isinstance(v, dict):
+        return {str(_canon_key(k)): _canon(x) for k, x in v.items()}
+    if isinstance(v, (list, tuple)):
+        return [_canon(x) for x in v]
+    if isinstance(v, (bool, np.bool_)):
+        return bool(v)
+    if isinstance(v, (int, np.integer)):
+        return int(v)
+    return v
+
+
+def _canon_key(k):
+    return tuple(int(x) for x in k) if isinstance(k, tuple) else (int(k) if isinstance(k, (int, np.integer)) else k)
+
+
 def snapshot(obs, info, reward=None, terminated=None, truncated=None, full_static=False):
     """One step's outputs.  Static planes (everything but visited / agent_location) are
     recorded only when `full_static` (at reset) -- they are still *checked* every step by
@@ -41,6 +59,7 @@ def snapshot(obs, info, reward=None, terminated=None, truncated=None, full_stati
         "rewards": [_reward_repr(info["Rewards"]["normal_reward"]),
                     _reward_repr(info["Rewards"]["outcome_reward"])],
         "flags": [bool(info["rule_status"][k]["passed"]) for k in RULE_NAMES],
+        "details": {k: _canon(info["rule_status"][k]["detail"]) for k in RULE_NAMES + ("_terminated", "_truncated")},
         "regions": {str(k): [int(v["area"]), {kk: int(vv) for kk, vv in v["symbol_counts"].items()},
                              {str(int(kk)): int(vv) for kk, vv in v["colors"].items()}]
                     for k, v in info["rule_status"]["_regions"].items()},
