@@ -153,15 +153,22 @@ typedef struct {                 /* all pointers are HOST pointers; copied by sp
 typedef struct SparcStore SparcStore;
 typedef struct SparcEnv SparcEnv;
 
-/* observation 'new' (SG.py:956-979), written in full every call, reference dtypes:
+/* observation 'new' (SG.py:956-979), written in full every call.
+ * format SPARC_OBS_REFERENCE (0, the reference's dtypes -- the bit-exact drop-in and the headline benchmark):
  *   base  int32 [n_envs][n_planes][slab_x][slab_y]   (one-hot planes, SG.py:272-277, 305-306)
  *   color int32 [n_envs][slab_x][slab_y]             (SG.py:279)
  *   info  int64 [n_envs][slab_x][slab_y]             (SG.py:280)
+ * format SPARC_OBS_COMPACT (1, same values in the narrowest types that hold them -- 3.5x fewer bytes for a
+ * policy that lives on the GPU; reported under its own algorithmic bytes, never mixed with the above):
+ *   base  uint8 [..], color uint8 [..], info int32 [..]   (same shapes)
  * contiguous, 16-byte aligned; any pointer may be NULL to skip that array. */
+enum { SPARC_OBS_REFERENCE = 0, SPARC_OBS_COMPACT = 1 };
 typedef struct {
-    int32_t* base_dev;
-    int32_t* color_dev;
-    int64_t* info_dev;
+    void*   base_dev;
+    void*   color_dev;
+    void*   info_dev;
+    int32_t format;      /* SPARC_OBS_* */
+    int32_t reserved;    /* 0 */
 } SparcObsOut;
 
 /* per-env step results (SG.py:1238); any pointer may be NULL */

@@ -68,17 +68,46 @@ struct SparcEnv {
 // dynamic shared memory of both kernels: tile heads (dyn rows + puzzle ids) | flat strings
 extern __shared__ __align__(128) uint32_t smem[];
 
+// Episode statistics: SPARC_STAT_ROWS rows of SPARC_N_STATS counters, a CTA adds into row blockIdx mod ROWS and
+// k_read_stats sums the rows.  (One row for everybody meant ~12,000 atomics per step on eight addresses; they
+// serialise in L2 and k_dyn is latency-bound as it is.)
+#ifndef SPARC_STAT_ROWS
+#define SPARC_STAT_ROWS 1024
+#endif
 __device__ __forceinline__ void reduce_stats(const KParams& p, bool have, const unsigned long long* my) {
+#ifndef DYN_NO_STATS      /* timing experiment only */
+    // steps / episodes / solved / failed / truncated / rules_pass are 0-or-1 per env: ballots, not shuffle sums;
+    // only a warp in which an episode ended (40 % of them at 1.6 % per env) reduces anything beyond `steps`
+    const unsigned full = 0xffffffffu;
+    const bool lead = (threadIdx.x & 31) == 0;
+    unsigned long long* row = p.sd.stats + (size_t)(blockIdx.x % SPARC_STAT_ROWS) * SPARC_N_STATS;
+    const unsigned live = __ballot_sync(full, have && my[SPARC_STAT_STEPS]);
+    if (lead && live) atomicAdd(row + SPARC_STAT_STEPS, (unsigned long long)__popc(live));
+    const bool ended = have && my[SPARC_STAT_EPISODES];
+    const unsigned done = __ballot_sync(full, ended);
+    if (!done) return;                                                          // warp-uniform
+    const unsigned solved = __ballot_sync(full, ended && my[SPARC_STAT_SOLVED]);
+    const unsigned failed = __ballot_sync(full, ended && my[SPARC_STAT_FAILED]);
+    const unsigned trunc = __ballot_sync(full, ended && my[SPARC_STAT_TRUNCATED]);
+    const unsigned rules = __ballot_sync(full, ended && my[SPARC_STAT_RULES_PASS]);
+    long long ret = ended ? (long long)my[SPARC_STAT_RETURN_CENTS] : 0ll;      // signed (two's complement in the counter)
+    unsigned long long len = ended ? my[SPARC_STAT_LENGTH] : 0ull;
 #pragma unroll
-    for (int k = 0; k < SPARC_N_STATS; k++) {                 // warp-reduce, one atomic per counter per warp
-        unsigned long long v = have ? my[k] : 0ull;
-#pragma unroll
-        for (int off = 16; off; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
-        if ((threadIdx.x & 31) == 0 && v) atomicAdd(p.sd.stats + k, v);
+    for (int off = 16; off; off >>= 1) { ret += __shfl_down_sync(full, ret, off); len += __shfl_down_sync(full, len, off); }
+    if (lead) {
+        atomicAdd(row + SPARC_STAT_EPISODES, (unsigned long long)__popc(done));
+        if (solved) atomicAdd(row + SPARC_STAT_SOLVED, (unsigned long long)__popc(solved));
+        if (failed) atomicAdd(row + SPARC_STAT_FAILED, (unsigned long long)__popc(failed));
+        if (trunc) atomicAdd(row + SPARC_STAT_TRUNCATED, (unsigned long long)__popc(trunc));
+        if (rules) atomicAdd(row + SPARC_STAT_RULES_PASS, (unsigned long long)__popc(rules));
+        if (ret) atomicAdd(row + SPARC_STAT_RETURN_CENTS, (unsigned long long)ret);
+        atomicAdd(row + SPARC_STAT_LENGTH, len);
     }
+#endif
 }
 
 // ---- simple kernel: one CTA = one tile (small batches: every CTA is resident at once) ----------
+template <int FMT>
 __global__ void __launch_bounds__(CTA_THREADS, SPARC_MINBLOCKS) k_env(const KParams p) {
     const StoreDev& st = p.st;
     const int tid = threadIdx.x;
@@ -101,9 +130,9 @@ __global__ void __launch_bounds__(CTA_THREADS, SPARC_MINBLOCKS) k_env(const KPar
     __syncthreads();
     encode_tile_stage1a(st, head, flats, p.tile, nE, p.obs, tid, CTA_THREADS);
     __syncthreads();
-    encode_tile_stage1b(st, head, flats, p.tile, nE, p.obs, tid, CTA_THREADS);
+    encode_tile_stage1b<FMT>(st, head, flats, p.tile, nE, p.obs, tid, CTA_THREADS);
     __syncthreads();
-    encode_tile_stage2(st, head, flats, p.tile, nE, env0, p.obs, tid, CTA_THREADS);
+    encode_tile_stage2<FMT>(st, head, flats, p.tile, nE, env0, p.obs, tid, CTA_THREADS);
 }
 
 // ---- split pair for big batches: k_dyn (latency bound) || k_encode (bandwidth bound) -------------
@@ -141,7 +170,16 @@ __global__ void __launch_bounds__(CTA_THREADS, DYN_MINBLOCKS) k_dyn(const KParam
 __global__ void __launch_bounds__(CTA_THREADS) k_val(const KParams p) {
     const uint32_t count = *p.vq_count;
     unsigned long long pass = 0;
+    // Snapshots are dealt out warp by warp (slot s -> warp s mod nwarps), not thread by thread: every snapshot is
+    // a different puzzle and path, so the lanes of a warp diverge and run one after the other -- the fewer
+    // snapshots share a warp, the shorter the kernel.
+    const uint32_t nwarps = gridDim.x * (CTA_THREADS / 32);
+    const uint32_t warp = blockIdx.x * (CTA_THREADS / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+#ifdef VAL_DENSE      /* experiment: the old thread-by-thread mapping */
     for (uint32_t slot = blockIdx.x * CTA_THREADS + threadIdx.x; slot < count; slot += gridDim.x * CTA_THREADS)
+#else
+    for (uint32_t slot = lane * nwarps + warp; slot < count; slot += 32 * nwarps)
+#endif
         pass += (unsigned long long)validate_queued(p, slot);
 #pragma unroll
     for (int off = 16; off; off >>= 1) pass += __shfl_down_sync(0xffffffffu, pass, off);
@@ -159,6 +197,7 @@ __global__ void __launch_bounds__(CTA_THREADS) k_val(const KParams p) {
 #ifndef ENC_MINBLOCKS
 #define ENC_MINBLOCKS 8
 #endif
+template <int FMT>
 __global__ void __launch_bounds__(ENC_THREADS, ENC_MINBLOCKS) k_encode(const KParams p, long long lo, long long hi) {
     const StoreDev& st = p.st;
     const int tid = threadIdx.x;
@@ -180,10 +219,10 @@ __global__ void __launch_bounds__(ENC_THREADS, ENC_MINBLOCKS) k_encode(const KPa
     __syncthreads();
     encode_tile_stage1a(st, head, flats, p.tile, nE, p.obs, tid, ENC_THREADS);
     __syncthreads();
-    encode_tile_stage1b(st, head, flats, p.tile, nE, p.obs, tid, ENC_THREADS);
+    encode_tile_stage1b<FMT>(st, head, flats, p.tile, nE, p.obs, tid, ENC_THREADS);
     __syncthreads();
 #endif
-    encode_tile_stage2(st, head, flats, p.tile, nE, env0, p.obs, tid, ENC_THREADS);
+    encode_tile_stage2<FMT>(st, head, flats, p.tile, nE, env0, p.obs, tid, ENC_THREADS);
 }
 
 // ---- ring kernel: one persistent, warp-specialised CTA per SM -------------------------------------
@@ -269,7 +308,7 @@ __device__ __forceinline__ void ring_expand_tile(const StoreDev& st, const uint3
     const uint32_t* rz = rc + RING_TILE * (st.Wc + 2);
     if (obs.base_dev) {
         const int L = st.L, Ws = st.W + 2, total = nE * L;
-        int32_t* out = obs.base_dev + (size_t)env0 * L;
+        int32_t* out = static_cast<int32_t*>(obs.base_dev) + (size_t)env0 * L;
         stream_blocks(reinterpret_cast<char*>(out), total >> 2, wc, nw, lane, stage, phase, [&](int c) {
             const uint32_t n = row_fetch(rb, 4u * (uint32_t)c, L, Ws, st.inv_L);
             return make_int4(n & 1, (n >> 1) & 1, (n >> 2) & 1, (n >> 3) & 1);
@@ -278,7 +317,7 @@ __device__ __forceinline__ void ring_expand_tile(const StoreDev& st, const uint3
     }
     if (obs.color_dev) {
         const int L = 4 * st.S, Ws = st.Wc + 2, total = nE * st.S;
-        int32_t* out = obs.color_dev + (size_t)env0 * st.S;
+        int32_t* out = static_cast<int32_t*>(obs.color_dev) + (size_t)env0 * st.S;
         stream_blocks(reinterpret_cast<char*>(out), total >> 2, wc, nw, lane, stage, phase, [&](int c) {
             const uint32_t n = row_fetch(rc, 16u * (uint32_t)c, L, Ws, st.inv_4S);
             return make_int4(n & 15, (n >> 4) & 15, (n >> 8) & 15, (n >> 12) & 15);
@@ -287,7 +326,7 @@ __device__ __forceinline__ void ring_expand_tile(const StoreDev& st, const uint3
     }
     if (obs.info_dev) {
         const int S = st.S, Ws = st.nv + 2, total = nE * S;
-        int64_t* out = obs.info_dev + (size_t)env0 * S;
+        int64_t* out = static_cast<int64_t*>(obs.info_dev) + (size_t)env0 * S;
         stream_blocks(reinterpret_cast<char*>(out), total >> 1, wc, nw, lane, stage, phase, [&](int c) {
             const uint32_t e0 = 2u * (uint32_t)c;
             const uint32_t m = row_fetch(rz, e0, S, Ws, st.inv_S) & 3u;
@@ -441,9 +480,16 @@ __global__ void k_init_state(StateDev sd, long long n, int n_puzzles) {
     sd.core[4 * i + 1] = 0; sd.core[4 * i + 2] = 0; sd.core[4 * i + 3] = 0;
 }
 
-__global__ void k_read_stats(unsigned long long* stats, long long* out, int clear) {
-    const int k = threadIdx.x;
-    if (k < SPARC_N_STATS) { out[k] = (long long)stats[k]; if (clear) stats[k] = 0; }
+__global__ void k_read_stats(unsigned long long* stats, long long* out, int clear) {     // <<<1, 32 * SPARC_N_STATS>>>
+    const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;                            // warp k sums counter k over the rows
+    unsigned long long v = 0;
+    for (int r = lane; r < SPARC_STAT_ROWS; r += 32) {
+        v += stats[(size_t)r * SPARC_N_STATS + k];
+        if (clear) stats[(size_t)r * SPARC_N_STATS + k] = 0;
+    }
+#pragma unroll
+    for (int off = 16; off; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+    if (lane == 0) out[k] = (long long)v;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -536,8 +582,10 @@ int sparc_env_create(SparcStore* store, int64_t n_envs, int traceback, int max_s
     {   // tiles above ~100 envs need more than the default 48 KB of dynamic shared memory
         const size_t shmem = (size_t)(tile_head_words(e->tile) + tile_flat_words(store->d, e->tile)) * sizeof(uint32_t);
         if (shmem > 48 * 1024) {
-            cudaError_t ae = cudaFuncSetAttribute(k_env, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem);
-            if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem);
+            cudaError_t ae = cudaFuncSetAttribute(k_env<SPARC_OBS_REFERENCE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem);
+            if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_env<SPARC_OBS_COMPACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem);
+            if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_encode<SPARC_OBS_REFERENCE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem);
+            if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_encode<SPARC_OBS_COMPACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem);
             if (ae != cudaSuccess) { delete e; return fail(SPARC_E_CUDA, "k_env shared memory: %s", cudaGetErrorString(ae)); }
         }
     }
@@ -596,7 +644,7 @@ int sparc_env_create(SparcStore* store, int64_t n_envs, int traceback, int max_s
     alloc((void**)&e->s.vis, n * 8 * 4);
     alloc((void**)&e->s.ep_ret, n * 4);
     if (traceback) alloc((void**)&e->s.moves, n * SPARC_MOVE_WORDS * 4);
-    alloc((void**)&e->s.stats, SPARC_N_STATS * 8);
+    alloc((void**)&e->s.stats, (size_t)SPARC_STAT_ROWS * SPARC_N_STATS * 8);
     alloc((void**)&e->sched, 16 * sizeof(unsigned int));   // [2..] cycle counters when built with -DRING_PROFILE
     alloc((void**)&e->act_stage, n);
     alloc((void**)&e->rew_stage, n * 4);
@@ -629,14 +677,18 @@ int sparc_env_destroy(SparcEnv* e) {
 static int launch_env(SparcEnv* e, KParams& p, void* stream) {
     p.st = e->store->d; p.sd = e->s; p.cfg = e->cfg; p.tile = e->tile;
     const int64_t n = e->cfg.n_envs;
-    const unsigned ntiles = (unsigned)((n + e->tile - 1) / e->tile);
+    if (p.obs.format != SPARC_OBS_REFERENCE && p.obs.format != SPARC_OBS_COMPACT) return fail(SPARC_E_ARG, "bad observation format%s");
+    // uint8 streams stay 16-byte aligned only when every tile starts at a multiple of 16 envs
+    const bool compact = p.obs.format == SPARC_OBS_COMPACT;
+    if (compact && p.tile < 16) p.tile = 16;
+    const unsigned ntiles = (unsigned)((n + p.tile - 1) / p.tile);
     if (e->split_chunks > 0) {
         // chunk c: [k_dyn on the side stream] -> event -> [k_encode on the caller's stream]
         cudaStream_t s0 = (cudaStream_t)stream;
         const bool any_obs = p.obs.base_dev || p.obs.color_dev || p.obs.info_dev;
         const int nc = e->split_chunks;
         const int64_t per = ((n + nc - 1) / nc + 127) / 128 * 128;       // chunk boundaries stay 16-B aligned in every stream
-        p.tile = e->enc_tile;
+        p.tile = (compact && e->enc_tile < 32) ? 32 : e->enc_tile;     // compact: 32 envs = 81 KB per CTA (measured: 16 -> 0.090, 32 -> 0.078, 64 -> 0.077 ms)
         const size_t shmem = (size_t)(tile_head_words(p.tile) + tile_flat_words(p.st, p.tile)) * sizeof(uint32_t);
         cudaStream_t sd = nc > 1 ? e->side : s0;                         // one chunk: plain back-to-back launches
         const bool defer = p.mode == 0 && e->vq && e->cfg.validate_mode == SPARC_VALIDATE_TERMINAL;
@@ -661,7 +713,11 @@ static int launch_env(SparcEnv* e, KParams& p, void* stream) {
             const bool fork_val = defer && last;
             const bool fork_copy = e->hostcopy.active && nc == 1;
             if (nc == 1 && (fork_val || fork_copy)) CU(cudaEventRecord(e->ev_start, s0));   // = k_dyn done
-            if (any_obs) k_encode<<<(unsigned)((hi - lo + p.tile - 1) / p.tile), ENC_THREADS, shmem, s0>>>(p, lo, hi);
+            if (any_obs) {
+                const unsigned egrid = (unsigned)((hi - lo + p.tile - 1) / p.tile);
+                if (compact) k_encode<SPARC_OBS_COMPACT><<<egrid, ENC_THREADS, shmem, s0>>>(p, lo, hi);
+                else k_encode<SPARC_OBS_REFERENCE><<<egrid, ENC_THREADS, shmem, s0>>>(p, lo, hi);
+            }
             if (fork_copy) {                                                 // results -> host beside k_encode
                 const size_t nn = (size_t)n;
                 CU(cudaStreamWaitEvent(e->copy_stream, e->ev_start, 0));
@@ -684,12 +740,14 @@ static int launch_env(SparcEnv* e, KParams& p, void* stream) {
         return SPARC_OK;
     }
     if (e->ring_grid > 0) {
+        if (compact) return fail(SPARC_E_ARG, "the ring kernel (SPARC_RING=1) writes the reference format only%s");
         p.tile = RING_TILE;
         const size_t shmem = (size_t)(4 * RING_PROD + RING_PROD * ring_slot_words(p.st) + RING_CONS * 2 * STAGE_WORDS) * sizeof(uint32_t);
         k_env_ring<<<(unsigned)e->ring_grid, RING_THREADS, shmem, (cudaStream_t)stream>>>(p, e->sched);
     } else {
-        const size_t shmem = (size_t)(tile_head_words(e->tile) + tile_flat_words(p.st, e->tile)) * sizeof(uint32_t);
-        k_env<<<ntiles, CTA_THREADS, shmem, (cudaStream_t)stream>>>(p);
+        const size_t shmem = (size_t)(tile_head_words(p.tile) + tile_flat_words(p.st, p.tile)) * sizeof(uint32_t);
+        if (compact) k_env<SPARC_OBS_COMPACT><<<ntiles, CTA_THREADS, shmem, (cudaStream_t)stream>>>(p);
+        else k_env<SPARC_OBS_REFERENCE><<<ntiles, CTA_THREADS, shmem, (cudaStream_t)stream>>>(p);
     }
     CU(cudaGetLastError());
     e->launches++;
@@ -721,9 +779,13 @@ int sparc_encode(SparcEnv* e, const SparcObsOut* obs, void* stream) {
     KParams p; memset(&p, 0, sizeof(p));
     p.st = e->store->d; p.sd = e->s; p.cfg = e->cfg; p.obs = *obs;
     const int64_t n = e->cfg.n_envs;
+    if (obs->format != SPARC_OBS_REFERENCE && obs->format != SPARC_OBS_COMPACT) return fail(SPARC_E_ARG, "bad observation format%s");
     p.tile = e->split_chunks > 0 ? e->enc_tile : (e->tile <= ENC_THREADS ? e->tile : 32);
+    if (obs->format == SPARC_OBS_COMPACT && p.tile < 32) p.tile = 32;
     const size_t shmem = (size_t)(tile_head_words(p.tile) + tile_flat_words(p.st, p.tile)) * sizeof(uint32_t);
-    k_encode<<<(unsigned)((n + p.tile - 1) / p.tile), ENC_THREADS, shmem, (cudaStream_t)stream>>>(p, 0, n);
+    const unsigned egrid = (unsigned)((n + p.tile - 1) / p.tile);
+    if (obs->format == SPARC_OBS_COMPACT) k_encode<SPARC_OBS_COMPACT><<<egrid, ENC_THREADS, shmem, (cudaStream_t)stream>>>(p, 0, n);
+    else k_encode<SPARC_OBS_REFERENCE><<<egrid, ENC_THREADS, shmem, (cudaStream_t)stream>>>(p, 0, n);
     CU(cudaGetLastError());
     e->launches++;
     return SPARC_OK;
@@ -742,7 +804,7 @@ int sparc_validate(SparcEnv* e, const uint8_t* mask_dev, uint16_t* flags_dev, in
 
 int sparc_stats(SparcEnv* e, int64_t* out_dev, int clear, void* stream) {
     if (!e || !out_dev) return fail(SPARC_E_ARG, "null argument%s");
-    k_read_stats<<<1, 32, 0, (cudaStream_t)stream>>>(e->s.stats, (long long*)out_dev, clear);
+    k_read_stats<<<1, 32 * SPARC_N_STATS, 0, (cudaStream_t)stream>>>(e->s.stats, (long long*)out_dev, clear);
     CU(cudaGetLastError());
     e->launches++;
     return SPARC_OK;

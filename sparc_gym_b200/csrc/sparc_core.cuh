@@ -834,6 +834,58 @@ SPARC_HD void expand_info(const StoreDev& st, const uint32_t* rows, const uint32
     }
 }
 
+// ---- compact format: uint8 planes / uint8 colour / int32 additional_info (same values, narrowest types) ----
+// 4 bits -> 4 bytes of 0/1 (bit i lands in byte i)
+SPARC_HD uint32_t spread4(uint32_t nib) { return ((nib & 15u) * 0x00204081u) & 0x01010101u; }
+// 4 nibbles (16 bits) -> 4 bytes
+SPARC_HD uint32_t nib4(uint32_t v) { return (v & 0xFu) | ((v & 0xF0u) << 4) | ((v & 0xF00u) << 8) | ((v & 0xF000u) << 12); }
+// planes: a 16-byte chunk = 16 elements = 16 stream bits
+SPARC_HD void expand_base_u8(const StoreDev& st, const uint32_t* rows, uint8_t* out_tile, int nE, int tid, int nthr) {
+    const int L = st.L, Ws = st.W + 2, total = nE * L, nchunks = total >> 4;
+    for (int c = tid; c < nchunks; c += nthr) {
+        const uint32_t n = row_fetch(rows, 16u * (uint32_t)c, L, Ws, st.inv_L);
+        sp_st4(reinterpret_cast<int32_t*>(out_tile + 16 * (size_t)c), (int32_t)spread4(n), (int32_t)spread4(n >> 4),
+               (int32_t)spread4(n >> 8), (int32_t)spread4(n >> 12));
+    }
+    for (int e = (nchunks << 4) + tid; e < total; e += nthr)
+        out_tile[e] = (uint8_t)(row_fetch(rows, (uint32_t)e, L, Ws, st.inv_L) & 1u);
+}
+// colour: a chunk = 16 elements = 64 stream bits = two word-aligned 32-bit fetches (each may sit in another env)
+SPARC_HD void expand_color_u8(const StoreDev& st, const uint32_t* rows, uint8_t* out_tile, int nE, int tid, int nthr) {
+    const int L = 4 * st.S, Ws = st.Wc + 2, total = nE * st.S, nchunks = total >> 4;
+    for (int c = tid; c < nchunks; c += nthr) {
+        const uint32_t lo = row_fetch(rows, 64u * (uint32_t)c, L, Ws, st.inv_4S);
+        const uint32_t hi = row_fetch(rows, 64u * (uint32_t)c + 32u, L, Ws, st.inv_4S);
+        sp_st4(reinterpret_cast<int32_t*>(out_tile + 16 * (size_t)c), (int32_t)nib4(lo), (int32_t)nib4(lo >> 16),
+               (int32_t)nib4(hi), (int32_t)nib4(hi >> 16));
+    }
+    for (int e = (nchunks << 4) + tid; e < total; e += nthr)
+        out_tile[e] = (uint8_t)(row_fetch(rows, 4u * (uint32_t)e, L, Ws, st.inv_4S) & 15u);
+}
+// additional_info: a chunk = 4 int32 elements; only marked nodes read their value
+SPARC_HD void expand_info_i32(const StoreDev& st, const uint32_t* rows, const uint32_t* tile_puzzle, int32_t* out_tile,
+                              int nE, int tid, int nthr) {
+    const int S = st.S, Ws = st.nv + 2, total = nE * S, nchunks = total >> 2;
+    for (int c = tid; c < nchunks; c += nthr) {
+        const uint32_t e0 = 4u * (uint32_t)c;
+        const uint32_t m = row_fetch(rows, e0, S, Ws, st.inv_S) & 15u;
+        int32_t v[4] = {0, 0, 0, 0};
+        if (m) {
+            int j = (int)sp_umulhi(e0, st.inv_S), r = (int)e0 - j * S;
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if ((m >> u) & 1u) v[u] = sp_ldg(st.info + (size_t)tile_puzzle[j] * S + r);
+                if (++r >= S) { r = 0; j++; }
+            }
+        }
+        sp_st4(out_tile + 4 * (size_t)c, v[0], v[1], v[2], v[3]);
+    }
+    for (int e = (nchunks << 2) + tid; e < total; e += nthr) {
+        const int jj = e / S, rr = e - jj * S;
+        out_tile[e] = sp_ldg(st.info + (size_t)tile_puzzle[jj] * S + rr);
+    }
+}
+
 // shared-memory words: per-tile header (dyn rows + puzzle ids) and the three row sets
 SPARC_HD int tile_head_words(int tile) { return tile * (SPARC_DYN_STRIDE + 1); }
 SPARC_HD int tile_flat_words(const StoreDev& st, int tile) { return tile * ((st.W + 2) + (st.Wc + 2) + (st.nv + 2)); }
@@ -850,6 +902,9 @@ SPARC_HD void encode_tile_stage1a(const StoreDev& st, const uint32_t* head, uint
     if (obs.color_dev) build_rows(ColorSrc{st, tile_puzzle}, rc, nE, st.inv_wsc, tid, nthr);
     if (obs.info_dev) build_rows(InfoNzSrc{st, tile_puzzle}, rz, nE, st.inv_wsz, tid, nthr);
 }
+// FMT = SPARC_OBS_* is a compile-time constant in the kernels: the reference-format encoder carries no trace of the
+// compact one (a run-time branch here cost 4 % of k_encode: 0.170 -> 0.176 ms, measured)
+template <int FMT = SPARC_OBS_REFERENCE>
 SPARC_HD void encode_tile_stage1b(const StoreDev& st, const uint32_t* head, uint32_t* flats, int tile, int nE,
                                   const SparcObsOut& obs, int tid, int nthr) {
     const uint32_t* dyn = head;
@@ -857,19 +912,29 @@ SPARC_HD void encode_tile_stage1b(const StoreDev& st, const uint32_t* head, uint
     uint32_t* rb = flats;
     uint32_t* rc = rb + tile * (st.W + 2);
     uint32_t* rz = rc + tile * (st.Wc + 2);
-    if (obs.base_dev) build_tails(PlaneSrc{st, dyn, tile_puzzle}, rb, nE, 4, tid, nthr);
-    if (obs.color_dev) build_tails(ColorSrc{st, tile_puzzle}, rc, nE, 16, tid, nthr);
-    if (obs.info_dev) build_tails(InfoNzSrc{st, tile_puzzle}, rz, nE, 2, tid, nthr);
+    // stream bits per fetch of the expand loops: 16-byte chunks of int32 / int32 / int64, or (compact) uint8 /
+    // uint8 fetched as two 32-bit halves / int32
+    constexpr bool cp = FMT == SPARC_OBS_COMPACT;
+    if (obs.base_dev) build_tails(PlaneSrc{st, dyn, tile_puzzle}, rb, nE, cp ? 16 : 4, tid, nthr);
+    if (obs.color_dev) build_tails(ColorSrc{st, tile_puzzle}, rc, nE, cp ? 32 : 16, tid, nthr);
+    if (obs.info_dev) build_tails(InfoNzSrc{st, tile_puzzle}, rz, nE, cp ? 4 : 2, tid, nthr);
 }
+template <int FMT = SPARC_OBS_REFERENCE>
 SPARC_HD void encode_tile_stage2(const StoreDev& st, const uint32_t* head, const uint32_t* flats, int tile, int nE,
                                  long long env0, const SparcObsOut& obs, int tid, int nthr) {
     const uint32_t* tile_puzzle = head + tile * SPARC_DYN_STRIDE;
     const uint32_t* rb = flats;
     const uint32_t* rc = rb + tile * (st.W + 2);
     const uint32_t* rz = rc + tile * (st.Wc + 2);
-    if (obs.base_dev) expand_base(st, rb, obs.base_dev + (size_t)env0 * st.L, nE, tid, nthr);
-    if (obs.color_dev) expand_color(st, rc, obs.color_dev + (size_t)env0 * st.S, nE, tid, nthr);
-    if (obs.info_dev) expand_info(st, rz, tile_puzzle, obs.info_dev + (size_t)env0 * st.S, nE, tid, nthr);
+    if (FMT == SPARC_OBS_COMPACT) {              // (env0 is a multiple of 16 here: every stream stays 16-byte aligned)
+        if (obs.base_dev) expand_base_u8(st, rb, static_cast<uint8_t*>(obs.base_dev) + (size_t)env0 * st.L, nE, tid, nthr);
+        if (obs.color_dev) expand_color_u8(st, rc, static_cast<uint8_t*>(obs.color_dev) + (size_t)env0 * st.S, nE, tid, nthr);
+        if (obs.info_dev) expand_info_i32(st, rz, tile_puzzle, static_cast<int32_t*>(obs.info_dev) + (size_t)env0 * st.S, nE, tid, nthr);
+        return;
+    }
+    if (obs.base_dev) expand_base(st, rb, static_cast<int32_t*>(obs.base_dev) + (size_t)env0 * st.L, nE, tid, nthr);
+    if (obs.color_dev) expand_color(st, rc, static_cast<int32_t*>(obs.color_dev) + (size_t)env0 * st.S, nE, tid, nthr);
+    if (obs.info_dev) expand_info(st, rz, tile_puzzle, static_cast<int64_t*>(obs.info_dev) + (size_t)env0 * st.S, nE, tid, nthr);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -334,6 +334,46 @@ def puzzle_array(row, text=None):
     return g
 
 
+SMALL_PIECES = [[[1, 1]], [[1], [1]], [[1, 1, 1]], [[1], [1], [1]], [[1, 1], [1, 0]], [[1, 1], [0, 1]],
+                [[1, 0], [1, 1]], [[0, 1], [1, 1]], [[1, 1], [1, 1]], [[1, 1, 1], [0, 1, 0]], [[1, 1, 1, 1]],
+                [[1, 0], [1, 0], [1, 1]], [[1, 1, 0], [0, 1, 1]], [[0, 1, 1], [1, 1, 0]], [[1], [1], [1], [1]],
+                [[1, 1, 1], [1, 0, 0]]]
+
+
+def gen_dense_poly_puzzle(w, h, seed, puzzle_id=None):
+    """A stress puzzle for the exact-fit search (SPaRC_Gym.py:738-895): the listed solution runs along the
+    border (start bottom-left, up, then right to the top-right end), so the whole w x h board is ONE region,
+    and it holds random small polyominoes of total area w*h -- about a dozen distinct pieces on 6x6.  Whether
+    they tile the board is what the search has to find out (1e3..1e5 nodes; most draws have no tiling).
+    Denser than anything `gen_puzzle` emits, on purpose."""
+    rng = np.random.default_rng([int(seed), 0xDE5E])
+    polys, tot = [], 0
+    while tot < w * h:
+        q = SMALL_PIECES[int(rng.integers(len(SMALL_PIECES)))]
+        a = int(np.array(q).sum())
+        if tot + a <= w * h and len(q) <= w and len(q[0]) <= h:
+            polys.append(q)
+            tot += a
+        elif w * h - tot == 1:
+            polys.append([[1]])
+            tot += 1
+    ids, cells = {}, []
+    for k, q in enumerate(polys):
+        sid = ids.setdefault(json.dumps(q), 20 + len(ids))
+        cx, cy = divmod(k, h)
+        cells.append({"position": {"x": 2 * cx + 1, "y": 2 * cy + 1},
+                      "properties": {"type": "poly", "color": COLOR_NAMES[k % 8], "polyshape": sid}})
+    path = [(0, y) for y in range(2 * h, -1, -1)] + [(x, 0) for x in range(1, 2 * w + 1)]
+    text = {"puzzle": {"start": {"x": 0, "y": 2 * h}, "end": {"x": 2 * w, "y": 0}, "cells": cells}}
+    row = {"id": puzzle_id or f"dense-{w}x{h}-{int(seed):06d}", "difficulty_level": 5,
+           "grid_size": {"width": int(w), "height": int(h)}, "solution_count": 1,
+           "solutions": [{"path": [{"x": x, "y": y} for x, y in path]}],
+           "polyshapes": json.dumps({str(v): json.loads(k) for k, v in ids.items()}),
+           "text_visualization": json.dumps(text)}
+    row["puzzle_array"] = puzzle_array(row, text)
+    return row
+
+
 def gen_pool(n, sizes, rules, seed0=0, **kw):
     """`n` rows; sizes is a list of (w, h) cycled over; row i uses seed seed0+i."""
     return [gen_puzzle(*sizes[i % len(sizes)], seed0 + i, rules, **kw) for i in range(n)]

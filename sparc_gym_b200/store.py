@@ -305,8 +305,10 @@ class PuzzleStore:
     def obs_elems_per_env(self):
         return self.n_planes * self.slab_x * self.slab_y
 
-    def algorithmic_bytes_per_step(self):
-        """B_alg of SURVEY.md section 8d: full observation rewrite in the reference dtypes + the state
-        record read and written + action/reward/flags."""
+    def algorithmic_bytes_per_step(self, obs_format="reference"):
+        """B_alg of SURVEY.md section 8d: full observation rewrite (reference dtypes int32 / int32 / int64, or the
+        compact uint8 / uint8 / int32 format, which is reported separately) + the state record read and written
+        + action/reward/flags."""
         S = self.slab_x * self.slab_y
-        return S * (4 * self.n_planes + 4 + 8) + 192 + 16
+        per_node = (4 * self.n_planes + 4 + 8) if obs_format == "reference" else (self.n_planes + 1 + 4)
+        return S * per_node + 192 + 16

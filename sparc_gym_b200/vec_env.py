@@ -64,11 +64,13 @@ class SparcVecEnv:
                    cursor, SG.py:1087; 0 = same puzzle again)
     validate       'terminal' | 'every_step' | 'never': when the rule validator
                    (SG.py:941-950) runs inside step(); its flags land in info['rule_flags']
+    obs_format     'reference' (int32 planes, int32 colour, int64 additional_info: the reference's dtypes,
+                   SG.py:272-280) or 'compact' (uint8 / uint8 / int32: same values, 3.5x fewer bytes)
     """
 
     def __init__(self, puzzles, num_envs, traceback=False, max_steps=2000, autoreset_mode="next_step",
                  puzzle_stride=1, validate="terminal", device="cuda:0", slab=None, planes="auto",
-                 write_obs=True):
+                 write_obs=True, obs_format="reference"):
         self.store = _as_store(puzzles, slab=slab, planes=planes) if not isinstance(puzzles, DeviceStore) else puzzles.host
         self.dstore = puzzles if isinstance(puzzles, DeviceStore) else DeviceStore(self.store, device)
         self.device = self.dstore.device
@@ -83,10 +85,13 @@ class SparcVecEnv:
                                                 abi.VALIDATE[validate], C.byref(handle)))
         self.handle = handle
         N, st, dev = self.num_envs, self.store, self.device
+        self.obs_format = obs_format
+        t_base, t_color, t_info = {"reference": (torch.int32, torch.int32, torch.int64),
+                                   "compact": (torch.uint8, torch.uint8, torch.int32)}[obs_format]
         self.obs = {
-            "base": torch.empty((N, st.n_planes, st.slab_x, st.slab_y), dtype=torch.int32, device=dev),
-            "color": torch.empty((N, st.slab_x, st.slab_y), dtype=torch.int32, device=dev),
-            "additional_info": torch.empty((N, st.slab_x, st.slab_y), dtype=torch.int64, device=dev),
+            "base": torch.empty((N, st.n_planes, st.slab_x, st.slab_y), dtype=t_base, device=dev),
+            "color": torch.empty((N, st.slab_x, st.slab_y), dtype=t_color, device=dev),
+            "additional_info": torch.empty((N, st.slab_x, st.slab_y), dtype=t_info, device=dev),
         }
         self.reward = torch.zeros(N, dtype=torch.float32, device=dev)
         self.reward_code = torch.zeros(N, dtype=torch.int8, device=dev)
@@ -98,8 +103,8 @@ class SparcVecEnv:
         self.agent_xy = torch.zeros((N, 2), dtype=torch.uint8, device=dev)
         self._stats = torch.zeros(abi.N_STATS, dtype=torch.int64, device=dev)
         self._obs_out = abi.ObsOut(self.obs["base"].data_ptr(), self.obs["color"].data_ptr(),
-                                   self.obs["additional_info"].data_ptr())
-        self._no_obs = abi.ObsOut(None, None, None)
+                                   self.obs["additional_info"].data_ptr(), abi.OBS_FORMATS[obs_format], 0)
+        self._no_obs = abi.ObsOut(None, None, None, 0, 0)
         self._step_out = abi.StepOut(self.reward.data_ptr(), self.reward_code.data_ptr(),
                                      self.terminated.data_ptr(), self.truncated.data_ptr(),
                                      self.legal_mask.data_ptr(), self.rule_flags.data_ptr(),

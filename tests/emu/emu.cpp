@@ -63,8 +63,13 @@ int emu_launch(const SparcStoreDesc* desc, uint32_t* core, uint32_t* vis, int32_
         }
         uint32_t* flats = dyn + tile_head_words(tile);
         for (int tid = 0; tid < nthr; tid++) encode_tile_stage1a(st, dyn, flats, tile, nE, p.obs, tid, nthr);
-        for (int tid = 0; tid < nthr; tid++) encode_tile_stage1b(st, dyn, flats, tile, nE, p.obs, tid, nthr);
-        for (int tid = 0; tid < nthr; tid++) encode_tile_stage2(st, dyn, flats, tile, nE, env0, p.obs, tid, nthr);
+        if (p.obs.format == SPARC_OBS_COMPACT) {
+            for (int tid = 0; tid < nthr; tid++) encode_tile_stage1b<SPARC_OBS_COMPACT>(st, dyn, flats, tile, nE, p.obs, tid, nthr);
+            for (int tid = 0; tid < nthr; tid++) encode_tile_stage2<SPARC_OBS_COMPACT>(st, dyn, flats, tile, nE, env0, p.obs, tid, nthr);
+        } else {
+            for (int tid = 0; tid < nthr; tid++) encode_tile_stage1b<SPARC_OBS_REFERENCE>(st, dyn, flats, tile, nE, p.obs, tid, nthr);
+            for (int tid = 0; tid < nthr; tid++) encode_tile_stage2<SPARC_OBS_REFERENCE>(st, dyn, flats, tile, nE, env0, p.obs, tid, nthr);
+        }
     }
     for (uint32_t slot = 0; slot < vq_count; slot++) stats[SPARC_STAT_RULES_PASS] += validate_queued(p, slot);
     return 0;

@@ -30,7 +30,8 @@ def build_emu():
 
 class EmuVecEnv:
     def __init__(self, puzzles, num_envs, traceback=False, max_steps=2000, autoreset_mode="next_step",
-                 puzzle_stride=1, validate="terminal", slab=None, planes="auto", tile=8, nthr=128, defer_validation=False):
+                 puzzle_stride=1, validate="terminal", slab=None, planes="auto", tile=8, nthr=128, defer_validation=False,
+                 obs_format="reference"):
         if not isinstance(puzzles, PuzzleStore):
             if puzzles and isinstance(puzzles[0], dict):
                 puzzles = ingest_rows(puzzles)
@@ -48,9 +49,10 @@ class EmuVecEnv:
         self.ep_ret = np.zeros(N, np.int32)
         self.moves = np.zeros((12, N), np.uint32) if traceback else None
         self.stats_acc = np.zeros(abi.N_STATS, np.uint64)
-        self.obs = {"base": np.full((N, st.n_planes, st.slab_x, st.slab_y), -7, np.int32),
-                    "color": np.full((N, st.slab_x, st.slab_y), -7, np.int32),
-                    "additional_info": np.full((N, st.slab_x, st.slab_y), -7, np.int64)}
+        t_base, t_color, t_info = {"reference": (np.int32, np.int32, np.int64), "compact": (np.uint8, np.uint8, np.int32)}[obs_format]
+        self.obs = {"base": np.full((N, st.n_planes, st.slab_x, st.slab_y), 249, t_base),
+                    "color": np.full((N, st.slab_x, st.slab_y), 249, t_color),
+                    "additional_info": np.full((N, st.slab_x, st.slab_y), -7, t_info)}
         self.reward = np.zeros(N, np.float32)
         self.reward_code = np.zeros(N, np.int8)
         self.terminated = np.zeros(N, np.uint8)
@@ -60,7 +62,8 @@ class EmuVecEnv:
         self.step_count = np.zeros(N, np.int32)
         self.agent_xy = np.zeros((N, 2), np.uint8)
         p = lambda a: a.ctypes.data
-        self._obs_out = abi.ObsOut(p(self.obs["base"]), p(self.obs["color"]), p(self.obs["additional_info"]))
+        self._obs_out = abi.ObsOut(p(self.obs["base"]), p(self.obs["color"]), p(self.obs["additional_info"]),
+                                   abi.OBS_FORMATS[obs_format], 0)
         self._step_out = abi.StepOut(p(self.reward), p(self.reward_code), p(self.terminated), p(self.truncated),
                                      p(self.legal_mask), p(self.rule_flags), p(self.step_count), p(self.agent_xy))
 

@@ -102,3 +102,35 @@ def test_encoder_is_tiling_invariant_and_handles_tiny_lattices():
                 a = rng.integers(0, 4, N).astype(np.uint8)
                 orc.step(a)
                 compare(env.step(a), orc.expected(), f"tile={tile} step {t}")
+
+
+def test_dense_polyomino_boards_vs_oracle():
+    """Stress puzzles for the exact-fit search (one region = the whole board, a dozen small pieces, 1e2..1e4
+    search nodes): the listed border path is replayed to the end, then the terminal validation must agree with
+    the oracle's restatement of the reference's search."""
+    from sparc_gym_b200.dataset import gen_dense_poly_puzzle
+    rows = [gen_dense_poly_puzzle(w, h, s) for (w, h, s) in [(3, 3, 0), (4, 4, 0), (4, 4, 3), (5, 5, 1), (5, 5, 2), (6, 6, 5)]]
+    make = lambda *a, **k: EmuVecEnv(*a, defer_validation=True, **k)
+    env, _ = run_lockstep(make, rows, 6, 26, False, 60, "disabled", "terminal", seed=1, follow=1.0)
+    assert env.stats()[0] == 6 and env.stats()[1] == 6          # six episodes, six listed solutions walked (+1)
+    assert 0 < env.stats()[7] < 6                               # some boards tile, some do not
+
+
+@pytest.mark.parametrize("tile,sizes", [(16, [(3, 3), (4, 4), (5, 5), (6, 6)]), (32, [(1, 1), (2, 3)]), (48, [(4, 4)])])
+def test_compact_observation_format_holds_the_same_values(tile, sizes):
+    """obs_format='compact' (uint8 planes, uint8 colour, int32 additional_info): same values as the reference
+    format, element for element, at every step -- incl. ragged last tiles and lattices whose env stride is odd."""
+    rows = gen_pool(7, sizes, RULES_FULL, seed0=60)
+    N = 2 * tile + 5
+    kw = dict(traceback=True, max_steps=25, autoreset_mode="same_step", validate="terminal")
+    a = EmuVecEnv(rows, N, tile=8 if tile == 16 else 4, **kw)
+    b = EmuVecEnv(rows, N, tile=tile, obs_format="compact", **kw)
+    assert b.obs["base"].dtype == np.uint8 and b.obs["color"].dtype == np.uint8 and b.obs["additional_info"].dtype == np.int32
+    a.reset(); b.reset()
+    rng = np.random.default_rng(4)
+    for t in range(40):
+        for k in a.obs:
+            assert np.array_equal(a.obs[k], b.obs[k]), (t, k)
+        act = rng.integers(0, 4, N).astype(np.uint8)
+        a.step(act); b.step(act)
+    assert np.array_equal(a.stats(), b.stats())

@@ -29,7 +29,15 @@ for rows in pools:
             rng = np.random.default_rng(tile)
             for t in range(40):
                 env.step(rng.integers(0, 5, N).astype(np.int64))
-            env.validate(region_map=True)
+            env.validate(region_map=True, region_fit=True)
+    # compact observation format (uint8 / uint8 / int32), deferred validation queue
+    for tile, N in ((16, 37), (64, 130)):
+        env = EmuVecEnv(rows, N, traceback=True, max_steps=17, autoreset_mode="same_step", validate="terminal",
+                        tile=tile, obs_format="compact", defer_validation=True)
+        env.reset()
+        rng = np.random.default_rng(tile)
+        for t in range(40):
+            env.step(rng.integers(0, 4, N).astype(np.uint8))
 print("sanitizer run ok")
 """ % (ROOT, HERE, os.path.join(ROOT, "oracle"))
 

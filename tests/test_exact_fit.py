@@ -139,3 +139,33 @@ def test_sweep_equals_reference_order_and_oracle():
         n_y += bool(ylops)
         worst = max(worst, it_sweep)
     assert n_fit > 300 and n - n_fit > 100 and n_y > 300, (n_fit, n_y, worst)
+
+
+def test_dense_boards_sweep_equals_reference_order():
+    """6x6 board, ~11 random small pieces of total area 36 (dataset.gen_dense_poly_puzzle's recipe): the sweep search
+    of the kernels and the reference-order search compiled from the same header agree, and the sweep stays within
+    a few 1e4 nodes on the hardest draws (the reference-order search is capped here by skipping draws it would
+    need > 2e6 nodes for)."""
+    from sparc_gym_b200.dataset import SMALL_PIECES
+    rng = np.random.default_rng(0)
+    region = [(2 * i + 1, 2 * j + 1) for i in range(6) for j in range(6)]
+    n = n_fit = worst = 0
+    for _ in range(60):
+        polys, tot = [], 0
+        while tot < 36:
+            q = SMALL_PIECES[int(rng.integers(len(SMALL_PIECES)))]
+            if tot + area(q) <= 36:
+                polys.append(q)
+                tot += area(q)
+            elif 36 - tot == 1:
+                break
+        if tot != 36:
+            continue
+        a, it = device_fit(0, 13, 13, region, polys, [])
+        worst = max(worst, it)
+        if it < 4000:                     # the reference-order search has no floor pruning: keep it to the easy draws
+            b, _ = device_fit(1, 13, 13, region, polys, [])
+            assert a == b, polys
+            n += 1
+            n_fit += a
+    assert n > 20 and 0 < n_fit and worst < 200000, (n, n_fit, worst)

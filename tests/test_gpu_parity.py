@@ -168,3 +168,56 @@ def test_vector_env_face_reset_options():
     assert env.single_observation_space is not None and env.num_envs == 12 and env.plane_keys[:4] == ["visited", "gaps", "agent_location", "target_location"]
     out = env.step(torch.zeros(12, dtype=torch.int64, device="cuda"))
     assert len(out) == 5 and out[1].shape == (12,)
+
+
+def test_dense_polyomino_boards_on_the_gpu(monkeypatch):
+    """Dense polyomino boards (1e2..1e4 exact-fit search nodes each) through the deferred validation queue:
+    flags and statistics must equal the CPU build of the same code."""
+    from emu.emu_env import EmuVecEnv
+    from fuzzrows import solution_actions
+    from sparc_gym_b200.dataset import gen_dense_poly_puzzle
+    monkeypatch.setenv("SPARC_SPLIT", "1")
+    rows = [gen_dense_poly_puzzle(6, 6, s) for s in range(24)] + [gen_dense_poly_puzzle(5, 5, s) for s in range(8)]
+    rows += gen_pool(8, [(4, 4), (6, 6)], RULES_FULL, seed0=500)
+    N = 640                                   # 16 envs per puzzle
+    kw = dict(traceback=False, max_steps=200, autoreset_mode="disabled", validate="terminal")
+    g = make_env(rows, N, **kw)
+    c = EmuVecEnv(rows, N, tile=32, **kw)
+    g.reset(); c.reset()
+    sols = [solution_actions(r, 0) for r in rows]
+    T = max(map(len, sols))
+    for t in range(T):
+        a = np.array([sols[i % len(rows)][t] if t < len(sols[i % len(rows)]) else 0 for i in range(N)], np.uint8)
+        go, gr, gt, gu, gi = g.step(torch.from_numpy(a).cuda())
+        co, cr, ct, cu, ci = c.step(a)
+        assert np.array_equal(to_np(gi["rule_flags"]).astype(np.uint16), ci["rule_flags"]), t
+        assert np.array_equal(to_np(gt), ct) and np.array_equal(to_np(gi["reward_code"]), ci["reward_code"]), t
+    st = to_np(g.stats())
+    assert np.array_equal(st, c.stats())
+    assert st[0] == N and st[1] == N and 0 < st[7] < N      # every env walked its listed solution; some boards tile
+
+
+@pytest.mark.parametrize("n_envs", [333, 9000])
+def test_compact_observation_format_on_the_gpu(n_envs):
+    """obs_format='compact' (uint8 / uint8 / int32) holds the same values as the reference-dtype observation,
+    element for element, through the fused kernel (333 envs) and the split k_dyn / k_encode step (9,000 envs);
+    sparc_encode rewrites it from the state alike."""
+    rows = gen_pool(12, [(3, 3), (4, 4), (5, 5), (6, 6)], RULES_FULL, seed0=60)
+    kw = dict(traceback=True, max_steps=25, autoreset_mode="same_step", validate="terminal")
+    a = make_env(rows, n_envs, **kw)
+    b = make_env(rows, n_envs, obs_format="compact", **kw)
+    assert b.obs["base"].dtype == torch.uint8 and b.obs["additional_info"].dtype == torch.int32
+    a.reset(); b.reset()
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    for t in range(45):
+        for k in a.obs:
+            assert torch.equal(a.obs[k].to(torch.int64), b.obs[k].to(torch.int64)), (t, k)
+        act = torch.randint(0, 4, (n_envs,), dtype=torch.uint8, device="cuda", generator=gen)
+        a.step(act); b.step(act)
+    snap = {k: v.clone() for k, v in b.obs.items()}
+    for v in b.obs.values():
+        v.fill_(77)
+    b.encode()
+    for k in snap:
+        assert torch.equal(snap[k], b.obs[k]), k
+    assert torch.equal(a.stats(), b.stats())
