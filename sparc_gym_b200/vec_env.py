@@ -245,10 +245,11 @@ class SparcVectorEnv(SparcVecEnv):
         st = self.store
         self.metadata = {"autoreset_mode": self.autoreset_mode}
         self.single_action_space = _spaces.Discrete(4)
+        d_base, d_color, d_info = (np.int32, np.int32, np.int64) if self.obs_format == "reference" else (np.uint8, np.uint8, np.int32)
         self.single_observation_space = _spaces.Dict({
-            "base": _spaces.Box(low=0, high=1, shape=(st.n_planes, st.slab_x, st.slab_y), dtype=np.int32),
-            "color": _spaces.Box(low=0, high=8, shape=(st.slab_x, st.slab_y), dtype=np.int32),
-            "additional_info": _spaces.Box(low=0, high=143632, shape=(st.slab_x, st.slab_y), dtype=np.int64)})
+            "base": _spaces.Box(low=0, high=1, shape=(st.n_planes, st.slab_x, st.slab_y), dtype=d_base),
+            "color": _spaces.Box(low=0, high=8, shape=(st.slab_x, st.slab_y), dtype=d_color),
+            "additional_info": _spaces.Box(low=0, high=143632, shape=(st.slab_x, st.slab_y), dtype=d_info)})
         self.action_space, self.observation_space = self.single_action_space, self.single_observation_space
         self.plane_keys = list(st.plane_keys)
 
