@@ -112,17 +112,17 @@ enum { SPARC_CB_CELLS = 0, SPARC_CB_STAR = 1, SPARC_CB_SQUARE = 2,
        SPARC_CB_COLOR1 = 5,    /* ... COLOR1+7 : cells of colour 1..8 (SG.py:310) */
        SPARC_N_CELL_BOARDS = 16 };
 
-typedef struct {                 /* 32 bytes */
-    uint64_t mask;               /* shape cells, bit = dx*8 + (dy - min_dy); anchor = lexicographically
-                                    first filled entry, array index 0 -> grid x (SG.py:856-871) */
+typedef struct {                 /* 32 bytes: one 16-byte load fetches what a placement needs */
+    uint64_t mask;               /* bits 0..55: shape cells, bit = dx*8 + (dy - min_dy); anchor = lexicographically
+                                    first filled entry, array index 0 -> grid x (SG.py:856-871);
+                                    bits 56..58: anchor_dy = -min_dy, the anchor's column inside the mask;
+                                    bits 59..61: flags -- bit0: larger than any 7x7 board, bit1: no filled entry,
+                                    bit2: the filled entries are 4-connected */
+    uint64_t anchors;            /* bits 0..55: cells (bit = 8cx + cy) of THIS puzzle's board on which the anchor may
+                                    sit with every shape cell in bounds (SG.py:880-883); bits 56..63: area = sum of
+                                    the shape array (SG.py:733) */
     uint64_t poly_cells;         /* cells holding a 'poly' instance of this shape (SG.py:716-736) */
     uint64_t ylop_cells;         /* cells holding a 'ylop' instance */
-    uint8_t  area;               /* sum of the shape array (SG.py:733) */
-    uint8_t  anchor_dy;          /* -min_dy: anchor column inside `mask` */
-    uint8_t  max_dx, span_y;     /* extent of `mask` */
-    uint8_t  flags;              /* bit0: cannot be placed on any 7x7 grid; bit1: no filled entry;
-                                    bit2: the filled entries are 4-connected */
-    uint8_t  pad[3];
 } SparcShape;
 
 /* trie of the first `solution_count` listed solution paths (SG.py:1205-1223, 1244-1265):

@@ -311,11 +311,37 @@ struct Cnt3 { uint64_t c0, c1, c2; };                      // bit-sliced per-cel
 SPARC_HD void cnt_add(Cnt3& c, uint64_t m) { uint64_t t = c.c0 & m; c.c0 ^= m; m = t; t = c.c1 & m; c.c1 ^= m; c.c2 ^= t; }
 SPARC_HD void cnt_sub(Cnt3& c, uint64_t m) { uint64_t t = ~c.c0 & m; c.c0 ^= m; m = t; t = ~c.c1 & m; c.c1 ^= m; c.c2 ^= t; }
 
-SPARC_HD uint64_t shape_place(const SparcShape& s, int cx, int cy, int w, int h) {
-    if (s.flags & 3) return 0;                              // unplaceable / empty
-    const int y0 = cy - (int)s.anchor_dy;
-    if (y0 < 0 || cx + (int)s.max_dx >= w || y0 + (int)s.span_y >= h) return 0;   // SG.py:880-883
-    return s.mask << (cx * 8 + y0);
+// SparcShape words: mask = cells (bits 0..55) | anchor_dy << 56 | flags << 59; anchors = cells of THIS puzzle's
+// board on which the shape's anchor may sit with every cell in bounds (bits 0..55, SG.py:880-883) | area << 56.
+// One 16-byte load fetches everything a placement needs.
+#define SPARC_CELLS56 0x00FFFFFFFFFFFFFFull
+struct ShapeW { uint64_t mask, anchors; };
+SPARC_HD ShapeW load_shape(const SparcShape* s) {
+#if defined(__CUDA_ARCH__)
+    const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(s));
+    return {v.x, v.y};
+#else
+    return {s->mask, s->anchors};
+#endif
+}
+SPARC_HD int shp_flags(uint64_t mask_word) { return (int)(mask_word >> 59) & 7; }
+SPARC_HD int shp_area(uint64_t anchors_word) { return (int)(anchors_word >> 56); }
+// cells covered when the shape's anchor sits on `cell` (0 = not placeable there)
+SPARC_HD uint64_t shape_at(const ShapeW& s, int cell) {
+    if (!((s.anchors >> cell) & 1ull)) return 0;
+    return (s.mask & SPARC_CELLS56) << (cell - ((int)(s.mask >> 56) & 7));
+}
+SPARC_HD uint64_t shape_place(const SparcShape& s, int cx, int cy) { return shape_at(load_shape(&s), cx * 8 + cy); }
+
+// 32 small counters (0..255) in four registers: instances per shape slot
+struct Cnt8 { uint64_t w[4]; };
+SPARC_HD uint64_t cnt8_word(const Cnt8& c, int k) { uint64_t r = c.w[0]; r = k == 1 ? c.w[1] : r; r = k == 2 ? c.w[2] : r; r = k == 3 ? c.w[3] : r; return r; }
+SPARC_HD int cnt8_get(const Cnt8& c, int s) { return (int)(cnt8_word(c, s >> 3) >> ((s & 7) * 8)) & 255; }
+SPARC_HD void cnt8_add(Cnt8& c, int s, int d) {              // d = +1 / -1 (or a first value into a zero slot)
+    const uint64_t v = (uint64_t)(long long)d << ((s & 7) * 8);
+    const int k = s >> 3;
+#pragma unroll
+    for (int i = 0; i < 4; i++) c.w[i] += (i == k) ? v : 0ull;
 }
 
 // exact-fit existence in the REFERENCE's search order (SG.py:738-895): all ylops first (any
@@ -331,7 +357,7 @@ SPARC_HD bool exact_fit_reference_order(uint64_t region, int w, int h, const Spa
     uint8_t fr_item[64], fr_pos[64];
     int ny = 0;
     for (int s = 0; s < ns; s++) {
-        const int empty = (shapes[s].flags & 2) != 0;       // zero-area shapes never touch the grid
+        const int empty = (shp_flags(shapes[s].mask) & 2) != 0;       // zero-area shapes never touch the grid
         rem[s] = empty ? 0 : n_poly[s];
         for (int k = 0; k < (empty ? 0 : (int)n_ylop[s]); k++) if (ny < SPARC_MAX_YLOPS) ylist[ny++] = (uint8_t)s;
     }
@@ -345,7 +371,7 @@ SPARC_HD bool exact_fit_reference_order(uint64_t region, int w, int h, const Spa
             for (int a = it; a < 64; a++) {
                 const int cx = a >> 3, cy = a & 7;
                 if (cx >= w || cy >= h) continue;
-                const uint64_t m = shape_place(sh, cx, cy, w, h);
+                const uint64_t m = shape_place(sh, cx, cy);
                 if (!m) continue;
                 cnt_add(c, m); fr_pos[level] = (uint8_t)a; level++; it = 0; found = true; break;
             }
@@ -355,7 +381,7 @@ SPARC_HD bool exact_fit_reference_order(uint64_t region, int w, int h, const Spa
             const int t = sp_ffsll(nz) - 1;
             for (int s = it; s < ns; s++) {
                 if (!rem[s]) continue;
-                const uint64_t m = shape_place(shapes[s], t >> 3, t & 7, w, h);
+                const uint64_t m = shape_place(shapes[s], t >> 3, t & 7);
                 if (!m || (m & ~nz)) continue;              // a covered cell would go positive (SG.py:822)
                 cnt_sub(c, m); rem[s]--; fr_item[level] = (uint8_t)s; fr_pos[level] = (uint8_t)t;
                 level++; it = 0; found = true; break;
@@ -366,11 +392,11 @@ SPARC_HD bool exact_fit_reference_order(uint64_t region, int w, int h, const Spa
         level--;                                            // backtrack
         if (level < ny) {
             const int a = fr_pos[level];
-            cnt_sub(c, shape_place(shapes[ylist[level]], a >> 3, a & 7, w, h));
+            cnt_sub(c, shape_place(shapes[ylist[level]], a >> 3, a & 7));
             it = a + 1;
         } else {
             const int s = fr_item[level], t = fr_pos[level];
-            cnt_add(c, shape_place(shapes[s], t >> 3, t & 7, w, h)); rem[s]++;
+            cnt_add(c, shape_place(shapes[s], t >> 3, t & 7)); rem[s]++;
             it = s + 1;
         }
     }
@@ -406,28 +432,32 @@ SPARC_HD uint64_t cnt4_eq(const Cnt4& c, int k) {
 // (canonical non-decreasing slot order) so that c ends at exactly zero, then move on.  A ylop
 // is therefore only ever tried where polys can absorb it, and a dead cell is detected once,
 // not once per ylop combination.
+// State lives in registers: the per-slot instance counters are packed (Cnt8), `have_*` has a bit per slot
+// with instances left so that only those are visited, and a candidate placement costs ONE 16-byte load
+// (beside the encoder every load waits behind its store stream: the search went at ~0.75 us per node when
+// each candidate read five shape fields and two counter bytes from memory).
 SPARC_HD bool exact_fit(uint64_t region, int w, int h, const SparcShape* shapes, int ns,
-                        const uint8_t* n_poly, const uint8_t* n_ylop) {
+                        const Cnt8& n_poly, const Cnt8& n_ylop) {
     SPARC_COUNT_FIT_CALL();
-    uint8_t rem_p[SPARC_MAX_SHAPES], rem_y[SPARC_MAX_SHAPES];
+    Cnt8 rem_p = n_poly, rem_y = n_ylop;
     uint8_t fr_cell[128], fr_q[128];                          // DFS edges: q < 2ns placement, 0xFF = advance
     int tot_p = 0, tot_y = 0;
-    for (int s = 0; s < ns; s++) {
-        const int empty = (shapes[s].flags & 2) != 0;         // zero-area shapes never touch the grid
-        rem_p[s] = empty ? 0 : n_poly[s];
-        rem_y[s] = empty ? 0 : n_ylop[s];
-        if ((shapes[s].flags & 1) && (rem_p[s] | rem_y[s])) return false;   // can never be placed
-        tot_p += rem_p[s]; tot_y += rem_y[s];
-    }
-    if (tot_y > SPARC_MAX_YLOPS) return false;                // (ingest guarantees this never happens)
+    uint32_t have_p = 0, have_y = 0, mono_slots = 0;
+    bool all_connected = true;
     // isolated-cell prune: once no ylop is left, a demanded cell with no demanded 4-neighbour can only be
     // covered by a one-cell poly (every other shape is 4-connected and would need a neighbour)
-    uint32_t mono_slots = 0;
-    bool all_connected = true;
     for (int s = 0; s < ns; s++) {
-        if (rem_p[s] && !(shapes[s].flags & 4)) all_connected = false;
-        if (shapes[s].mask == 1ull) mono_slots |= 1u << s;
+        const ShapeW sh = load_shape(shapes + s);
+        const int fl = shp_flags(sh.mask);
+        int np = cnt8_get(rem_p, s), ny = cnt8_get(rem_y, s);
+        if (fl & 2) { cnt8_add(rem_p, s, -np); cnt8_add(rem_y, s, -ny); np = ny = 0; }   // zero-area shapes never touch the grid
+        if ((np | ny) && !(sh.anchors & SPARC_CELLS56)) return false;       // fits nowhere on this board
+        tot_p += np; tot_y += ny;
+        if (np) { have_p |= 1u << s; if (!(fl & 4)) all_connected = false; }
+        if (ny) have_y |= 1u << s;
+        if ((sh.mask & SPARC_CELLS56) == 1ull) mono_slots |= 1u << s;
     }
+    if (tot_y > SPARC_MAX_YLOPS) return false;                // (ingest guarantees this never happens)
     Cnt4 c = {region, 0, 0, 0};
     uint64_t grid = 0;
     for (int cx = 0; cx < w; cx++) grid |= ((1ull << h) - 1ull) << (cx * 8);
@@ -437,39 +467,46 @@ SPARC_HD bool exact_fit(uint64_t region, int w, int h, const SparcShape* shapes,
         SPARC_COUNT_FIT();
         const int n = cnt4_get(c, cell);
         const uint64_t later = grid & ~((2ull << cell) - 1ull);               // cells after `cell`
+        const uint64_t floor_cells = cnt4_eq(c, -tot_y) & later;              // later cells already at what ylops can lift
         bool found = false;
-        for (int qq = (tot_y == 0 && q < ns) ? ns : q; qq < 2 * ns; qq++) {
-            if (qq < ns) {                                                    // anchor a ylop here
-                if (!rem_y[qq] || n + 1 > tot_p) continue;
-                const uint64_t m = shape_place(shapes[qq], cell >> 3, cell & 7, w, h);
+        if (q < ns && n + 1 <= tot_p) {                                       // anchor a ylop here (slots >= q)
+            for (uint32_t cand = have_y & (0xFFFFFFFFu << q); cand; cand &= cand - 1) {
+                const int s = sp_ffs(cand) - 1;
+                const uint64_t m = shape_at(load_shape(shapes + s), cell);
                 if (!m) continue;
-                // one ylop fewer can lift later cells: those already at the floor would be lost
-                if (cnt4_eq(c, -tot_y) & later & ~m) continue;
-                cnt4_add(c, m); rem_y[qq]--; tot_y--;
-            } else {                                                          // anchor a poly here
-                const int s = qq - ns;
-                if (n <= 0) break;                                            // nothing left to cover at this cell
-                if (!rem_p[s]) continue;
-                const uint64_t m = shape_place(shapes[s], cell >> 3, cell & 7, w, h);
+                if (floor_cells & ~m) continue;               // one ylop fewer can lift later cells: those at the floor would be lost
+                cnt4_add(c, m); cnt8_add(rem_y, s, -1); tot_y--;
+                if (!cnt8_get(rem_y, s)) have_y &= ~(1u << s);
+                fr_cell[level] = (uint8_t)cell; fr_q[level] = (uint8_t)s; level++;
+                q = s; found = true;
+                break;
+            }
+        }
+        if (!found && n > 0) {                                                // anchor a poly here (slots >= q - ns)
+            const int q2 = q > ns ? q - ns : 0;
+            for (uint32_t cand = q2 < 32 ? have_p & (0xFFFFFFFFu << q2) : 0u; cand; cand &= cand - 1) {
+                const int s = sp_ffs(cand) - 1;
+                const uint64_t m = shape_at(load_shape(shapes + s), cell);
                 if (!m) continue;
-                if (cnt4_eq(c, -tot_y) & later & m) continue;                 // would sink below what ylops can lift
-                cnt4_sub(c, m); rem_p[s]--; tot_p--;
+                if (floor_cells & m) continue;                // would sink below what ylops can lift
+                cnt4_sub(c, m); cnt8_add(rem_p, s, -1); tot_p--;
                 if (tot_y == 0 && all_connected) {
                     const uint64_t D = (c.b0 | c.b1 | c.b2) & ~c.b3;          // cells still demanded
                     const uint64_t iso = D & ~((D << 1) | (D >> 1) | (D << 8) | (D >> 8));
                     if (iso) {
                         int monos = 0;
-                        for (uint32_t ms = mono_slots; ms; ms &= ms - 1) monos += rem_p[sp_ffs(ms) - 1];
-                        if (sp_popcll(iso) > monos) { cnt4_add(c, m); rem_p[s]++; tot_p++; continue; }
+                        for (uint32_t ms = mono_slots; ms; ms &= ms - 1) monos += cnt8_get(rem_p, sp_ffs(ms) - 1);
+                        if (sp_popcll(iso) > monos) { cnt4_add(c, m); cnt8_add(rem_p, s, 1); tot_p++; continue; }
                     }
                 }
+                if (!cnt8_get(rem_p, s)) have_p &= ~(1u << s);
+                fr_cell[level] = (uint8_t)cell; fr_q[level] = (uint8_t)(ns + s); level++;
+                q = ns + s; found = true;
+                break;
             }
-            fr_cell[level] = (uint8_t)cell; fr_q[level] = (uint8_t)qq; level++;
-            q = qq; found = true;
-            break;
         }
         if (found) continue;
-        if (cnt4_get(c, cell) == 0) {                                         // settled: advance
+        if (n == 0) {                                                         // settled: advance
             const uint64_t open = (c.b0 | c.b1 | c.b2 | c.b3) & later;        // later cells with non-zero demand
             if (tot_p + tot_y == 0) { if (!open) return true; }               // nothing left and nothing demanded
             else if (later && (tot_y > 0 || open)) {
@@ -486,8 +523,8 @@ SPARC_HD bool exact_fit(uint64_t region, int w, int h, const SparcShape* shapes,
             cell = fr_cell[level];
             const int qq = fr_q[level];
             if (qq == 0xFF) continue;                                         // advance was the last child
-            if (qq < ns) { cnt4_sub(c, shape_place(shapes[qq], cell >> 3, cell & 7, w, h)); rem_y[qq]++; tot_y++; }
-            else { cnt4_add(c, shape_place(shapes[qq - ns], cell >> 3, cell & 7, w, h)); rem_p[qq - ns]++; tot_p++; }
+            if (qq < ns) { cnt4_sub(c, shape_at(load_shape(shapes + qq), cell)); cnt8_add(rem_y, qq, 1); tot_y++; have_y |= 1u << qq; }
+            else { cnt4_add(c, shape_at(load_shape(shapes + qq - ns), cell)); cnt8_add(rem_p, qq - ns, 1); tot_p++; have_p |= 1u << (qq - ns); }
             q = qq + 1;
             break;
         }
@@ -629,12 +666,14 @@ SPARC_HD int validate_env(const StoreDev& st, uint32_t puzzle, const uint32_t* v
         }
         // polys / ylops (SG.py:648-710)
         if (h.n_shapes && (poly_ok || region_fit)) {
-            uint8_t np[SPARC_MAX_SHAPES], nyl[SPARC_MAX_SHAPES];
+            Cnt8 np = {{0, 0, 0, 0}}, nyl = {{0, 0, 0, 0}};
             int net = 0, any = 0;
             for (int s = 0; s < h.n_shapes; s++) {
                 const int a = sp_popcll(sp_ldg(&shapes[s].poly_cells) & R), b = sp_popcll(sp_ldg(&shapes[s].ylop_cells) & R);
-                np[s] = (uint8_t)a; nyl[s] = (uint8_t)b; any |= a | b;
-                net += (a - b) * (int)shapes[s].area;
+                if (a | b) {
+                    cnt8_add(np, s, a); cnt8_add(nyl, s, b); any = 1;
+                    net += (a - b) * shp_area(sp_ldg(&shapes[s].anchors));
+                }
             }
             if (any) {
                 int verdict = SPARC_FIT_OK;

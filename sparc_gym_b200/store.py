@@ -39,9 +39,7 @@ HEADER_DTYPE = np.dtype([("X", "u1"), ("Y", "u1"), ("start_x", "u1"), ("start_y"
                          ("target_x", "u1"), ("target_y", "u1"), ("n_shapes", "u1"), ("flags", "u1"),
                          ("shape_off", "<u4"), ("trie_root", "<u4"), ("solution_count", "<i4"),
                          ("difficulty", "<i4"), ("reserved", "<u4", (2,))])
-SHAPE_DTYPE = np.dtype([("mask", "<u8"), ("poly_cells", "<u8"), ("ylop_cells", "<u8"),
-                        ("area", "u1"), ("anchor_dy", "u1"), ("max_dx", "u1"), ("span_y", "u1"),
-                        ("flags", "u1"), ("pad", "u1", (3,))])
+SHAPE_DTYPE = np.dtype([("mask", "<u8"), ("anchors", "<u8"), ("poly_cells", "<u8"), ("ylop_cells", "<u8")])
 assert HEADER_DTYPE.itemsize == 32 and SHAPE_DTYPE.itemsize == 32
 
 
@@ -63,9 +61,11 @@ def _cell_board(bits_xy):
     return v
 
 
-def shape_slot(arr):
-    """Anchor-normalised mask of a polyshape array exactly as `_get_offsets` (SG.py:856-871):
-    index 0 of the array runs along grid x; anchor = first filled entry in (x, y) order."""
+def shape_slot(arr, w=7, h=7):
+    """Shape record (SparcShape) of a polyshape array on a w x h board of rule cells: the anchor-normalised mask
+    exactly as `_get_offsets` (SG.py:856-871) -- index 0 of the array runs along grid x, anchor = first filled
+    entry in (x, y) order -- and the cells on which that anchor may sit with everything in bounds (SG.py:880-883).
+    mask = cells | anchor_dy << 56 | flags << 59; anchors = cells | area << 56."""
     a = np.array(arr)
     if a.ndim != 2:
         raise ValueError(f"polyshape array must be 2-D, got shape {a.shape}")
@@ -73,23 +73,24 @@ def shape_slot(arr):
         raise ValueError("polyshape arrays must be 0/1")
     xs, ys = np.nonzero(a == 1)
     rec = np.zeros((), SHAPE_DTYPE)
-    rec["area"] = int(a.sum())
+    area = int(a.sum())
+    if area > 255:
+        raise ValueError("polyshape with more than 255 filled entries")
+    rec["anchors"] = area << 56
     if len(xs) == 0:
-        rec["flags"] = 2
+        rec["mask"] = 2 << 59
         return rec
     ax = xs.min()
     ay = ys[xs == ax].min()
     dx, dy = xs - ax, ys - ay
     min_dy = int(dy.min())
     max_dx, span_y = int(dx.max()), int(dy.max()) - min_dy
-    rec["anchor_dy"], rec["max_dx"], rec["span_y"] = -min_dy, min(max_dx, 255), min(span_y, 255)
     if max_dx > 6 or span_y > 6:
-        rec["flags"] = 1               # larger than any supported grid: never placeable
+        rec["mask"] = 1 << 59          # larger than any supported board: never placeable
         return rec
     m = 0
     for i, j in zip(dx.tolist(), (dy - min_dy).tolist()):
         m |= 1 << (i * 8 + j)
-    rec["mask"] = m
     # bit2: the filled entries are 4-connected (lets the exact-fit search prune isolated cells)
     cells = set(zip(dx.tolist(), (dy - min_dy).tolist()))
     seen, todo = set(), [next(iter(cells))]
@@ -99,8 +100,15 @@ def shape_slot(arr):
             continue
         seen.add(c)
         todo += [n for n in ((c[0] + 1, c[1]), (c[0] - 1, c[1]), (c[0], c[1] + 1), (c[0], c[1] - 1)) if n in cells]
-    if seen == cells:
-        rec["flags"] = int(rec["flags"]) | 4
+    flags = 4 if seen == cells else 0
+    ady = -min_dy
+    rec["mask"] = m | (ady << 56) | (flags << 59)
+    anchors = 0
+    for cx in range(w):
+        for cy in range(h):
+            if cy - ady >= 0 and cx + max_dx < w and cy - ady + span_y < h:
+                anchors |= 1 << (cx * 8 + cy)
+    rec["anchors"] = anchors | (area << 56)
     return rec
 
 
@@ -276,7 +284,7 @@ class PuzzleStore:
                     if not (x % 2 and y % 2):
                         continue                                  # off-cell: region id -1, ignored (SG.py:664-667)
                     if name not in slots:
-                        slots[name] = shape_slot(pz.polyshapes[name])
+                        slots[name] = shape_slot(pz.polyshapes[name], (pz.X - 1) // 2, (pz.Y - 1) // 2)
                     bit = np.uint64(1 << ((x // 2) * 8 + (y // 2)))
                     if pz.planes["poly"][x, y] == 1:
                         slots[name]["poly_cells"] |= bit
@@ -293,7 +301,7 @@ class PuzzleStore:
             # biggest shapes first: the exact-fit search tries slots in this order, and placing
             # the rigid pieces early finds tilings (or dead ends) much sooner.  The answer does
             # not depend on the order (the reference's own order is by dataset position).
-            shapes.extend(sorted(slots.values(), key=lambda r: -int(r["area"])))
+            shapes.extend(sorted(slots.values(), key=lambda r: -(int(r["anchors"]) >> 56)))
 
         self.shapes = np.array(shapes, SHAPE_DTYPE) if shapes else np.zeros(1, SHAPE_DTYPE)
         self.n_shapes_total = len(shapes)

@@ -27,7 +27,7 @@ def device_fit(which, X, Y, region, polys, ylops):
         names.setdefault(json.dumps(a), len(names))
     slots = np.zeros(max(len(names), 1), SHAPE_DTYPE)
     for k, i in names.items():
-        slots[i] = shape_slot(json.loads(k))
+        slots[i] = shape_slot(json.loads(k), (X - 1) // 2, (Y - 1) // 2)
     npoly = np.zeros(32, np.uint8)
     nylop = np.zeros(32, np.uint8)
     for a in polys:

@@ -16,4 +16,4 @@ CMD="python bench.py --steps 8 --warmup 200 --no-e2e --no-cpu-baseline --no-grap
 $CMD > gpurun_out/plain.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -s 600 -c 40 --csv --log-file gpurun_out/r1_launches.csv $CMD > gpurun_out/ncu1.log 2>&1; echo ncu1=$?
 $CMD > gpurun_out/plain2.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:'k_encode|k_dyn|k_val' -s 606 -c 6 -o gpurun_out/r1_prof $CMD > gpurun_out/ncu2.log 2>&1; echo ncu2=$?
 CMDC="python bench.py --steps 8 --warmup 200 --no-e2e --no-cpu-baseline --no-graph --no-extra --obs-format compact"
-$CMDC > gpurun_out/plain3.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:'k_encode' -s 606 -c 2 -o gpurun_out/r1_prof_compact $CMDC > gpurun_out/ncu3.log 2>&1; echo ncu3=$?
+$CMDC > gpurun_out/plain3.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:'k_encode' -s 202 -c 2 -o gpurun_out/r1_prof_compact $CMDC > gpurun_out/ncu3.log 2>&1; echo ncu3=$?
