@@ -104,6 +104,33 @@ def test_encoder_is_tiling_invariant_and_handles_tiny_lattices():
                 compare(env.step(a), orc.expected(), f"tile={tile} step {t}")
 
 
+def max_size_rows():
+    """Pools at the ingest limit (7x7 cells = 15x15 lattice, SPARC_MAX_DIM) and non-square boards next to it:
+    generated full-rule puzzles plus fuzz rows (shape ids colliding with triangle counts, Q10); fuzz rows over
+    the documented ylop-instance limit are what ingest rejects, so they are left out here."""
+    from sparc_gym_b200.ingest import ingest_rows
+    from sparc_gym_b200.store import PuzzleStore
+    gen = gen_pool(6, [(7, 7), (7, 5), (2, 7), (6, 7)], RULES_FULL, seed0=300)
+    fuzz = []
+    for s in range(500, 560):
+        r = fuzz_row(s, max_cells=7, n_colors=8)
+        try:
+            PuzzleStore(ingest_rows([r]))
+        except ValueError as ex:
+            assert "ylop instances" in str(ex), ex
+            continue
+        fuzz.append(r)
+    assert len(fuzz) > 40 and any(r["grid_size"]["width"] == 7 or r["grid_size"]["height"] == 7 for r in fuzz)
+    return gen, fuzz
+
+
+def test_maximum_lattice_and_non_square_boards():
+    gen, fuzz = max_size_rows()
+    env, _ = run_lockstep(EmuVecEnv, gen, 12, 140, True, 120, "disabled", "every_step", seed=9, follow=0.97)
+    assert (env.store.slab_x, env.store.slab_y) == (15, 15) and env.stats()[1] > 0      # some listed solutions walked
+    run_lockstep(EmuVecEnv, fuzz, len(fuzz), 60, True, 50, "disabled", "every_step", seed=4)
+
+
 def test_dense_polyomino_boards_vs_oracle():
     """Stress puzzles for the exact-fit search (one region = the whole board, a dozen small pieces, 1e2..1e4
     search nodes): the listed border path is replayed to the end, then the terminal validation must agree with

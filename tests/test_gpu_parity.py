@@ -6,7 +6,7 @@ import torch
 
 from fuzzrows import fuzz_row
 from parity import to_np
-from test_emu_parity import run_lockstep
+from test_emu_parity import max_size_rows, run_lockstep
 from sparc_gym_b200.dataset import RULES_FULL, RULES_GAPS_DOTS, gen_pool
 
 pytestmark = pytest.mark.gpu
@@ -39,6 +39,29 @@ def test_autoreset_next_step_cycles_puzzles():
     env, orc = run_lockstep(make_env, rows, 10, 120, False, 25, "next_step", "terminal", seed=9, follow=0.3)
     st = to_np(env.stats())
     assert st[0] > 10 and st[4] > 0
+
+
+def test_maximum_lattice_and_non_square_boards():
+    """15x15 lattices (SPARC_MAX_DIM) and non-square boards, generated and fuzzed, under the fused and the split step."""
+    gen, fuzz = max_size_rows()
+    env, _ = run_lockstep(make_env, gen, 12, 140, True, 120, "disabled", "every_step", seed=9, follow=0.97)
+    assert (env.store.slab_x, env.store.slab_y) == (15, 15) and to_np(env.stats())[1] > 0
+    run_lockstep(make_env, fuzz, len(fuzz), 60, True, 50, "disabled", "every_step", seed=4)
+    # the split step (>= 8,192 envs) on the 15x15 slab against the CPU build of the same device code
+    from emu.emu_env import EmuVecEnv
+    N, kw = 8192 + 5, dict(traceback=True, max_steps=30, autoreset_mode="same_step", validate="terminal")
+    g, c = make_env(gen + fuzz, N, **kw), EmuVecEnv(gen + fuzz, N, tile=32, **kw)
+    g.reset(); c.reset()
+    rng = np.random.default_rng(1)
+    for t in range(40):
+        a = rng.integers(0, 4, N).astype(np.uint8)
+        go, gr, gt, gu, gi = g.step(torch.from_numpy(a).cuda())
+        co, cr, ct, cu, ci = c.step(a)
+        for k in go:
+            assert np.array_equal(to_np(go[k]), co[k]), (t, k)
+        assert np.array_equal(to_np(gi["reward_code"]), ci["reward_code"]) and np.array_equal(to_np(gt), ct), t
+        assert np.array_equal(to_np(gu), cu) and np.array_equal(to_np(gi["rule_flags"]).astype(np.uint16), ci["rule_flags"]), t
+    assert np.array_equal(to_np(g.stats()), c.stats()) and c.stats()[0] > 500
 
 
 @pytest.fixture(params=[("0", "0", "8"), ("0", "1", "32"), ("0", "0", "128"), ("3", "0", "8"), ("4", "0", "32"), ("1", "0", "4")],
