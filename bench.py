@@ -197,8 +197,9 @@ def main():
             steps_rates.append(cpu_baseline(args.workload, budget_s=min(args.cpu_seconds, 10.0)))
         best = max(steps_rates, key=lambda d: d["value"])
         print(json.dumps({"impl": "reference", "metric": "env-steps/sec (whole box)", "value": best["value"],
-                          "unit": "env-steps/s", "n_gpus": 0, "steps": len(steps_rates), "warmup": 0,
-                          "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "unit": "env-steps/s", "n_gpus": args.gpus, "steps": len(steps_rates), "warmup": 0,
+                          "ms_per_step": round(1e3 * min(args.cpu_seconds, 10.0), 1),      # one step = one bounded CPU sample
+                          "host_only": True, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                           "dtype": "int32", "data": "synthetic",
                           "config": {"workload": args.workload, "description": desc, "traceback": traceback,
                                      "max_steps": max_steps},
