@@ -527,6 +527,9 @@ int sparc_store_create(const SparcStoreDesc* desc, int device, SparcStore** out)
     d.n_puzzles = desc->n_puzzles; d.SX = desc->slab_x; d.SY = desc->slab_y; d.S = d.SX * d.SY;
     d.P = desc->n_planes; d.L = d.P * d.S; d.W = (d.L + 31) / 32;
     if (desc->words_per_puzzle != d.W) { delete s; return fail(SPARC_E_ARG, "words_per_puzzle mismatch%s"); }
+    if ((uint64_t)desc->n_puzzles * (uint64_t)(d.W + 2) >= (1ull << 32)) {        // the encoder indexes the pool with 32-bit word offsets
+        delete s; return fail(SPARC_E_ARG, "pool too large for 32-bit word offsets%s");
+    }
     d.nv = (d.S + 31) / 32;
     d.inv_L = (uint32_t)((1ull << 32) / (uint64_t)d.L) + 1u;
     d.inv_S = (uint32_t)((1ull << 32) / (uint64_t)d.S) + 1u;

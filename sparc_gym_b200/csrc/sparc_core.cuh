@@ -701,11 +701,10 @@ SPARC_HD int validate_env(const StoreDev& st, uint32_t puzzle, const uint32_t* v
 //   chunk c by thread c mod nthr, so a warp store covers 512 contiguous bytes.
 //
 //   Shared-memory staging ("rows"): for each stream, env j's bit string (L bits: 1 bit per base
-//   element, 4 per colour element, 1 "non-zero" bit per info element) is stored in its own row,
-//   shifted left by o_j = (j*L) mod 32.  Bit g of the tile-wide stream (g = j*L + r) then sits
-//   at row-bit o_j + r, which is congruent to g mod 32: the bits of a chunk never straddle a word
-//   and one LDS + one shift fetches them.  The few bits of env j+1 that share env j's last chunk
-//   are appended to row j ("tail").
+//   element, 4 per colour element, 1 "non-zero" bit per info element) is stored in its own row
+//   of W+2 words.  Bit g of the tile-wide stream (g = j*L + r) sits at row-bit r of row j: two
+//   LDS + one funnel shift fetch the 32 bits from there on.  The few bits of env j+1 that share
+//   env j's last chunk are appended to row j ("tail").
 //   dyn : SPARC_DYN_STRIDE words per env: visited plane (dense, 8 words) + bit index of the agent
 // ---------------------------------------------------------------------------------------------
 #define SPARC_DYN_STRIDE 9
@@ -737,16 +736,15 @@ struct PlaneSrc {                       // the P one-hot planes: static planes o
     const StoreDev& st; const uint32_t* dyn; const uint32_t* tile_puzzle;
     SPARC_HD int L() const { return st.L; }
     SPARC_HD int W() const { return st.W; }
+    // (32-bit word offsets into the store arrays: n_puzzles * W < 2^32 is checked by sparc_store_create)
     SPARC_HD uint32_t raw(int j, int k) const {                 // the global-memory part (issued early, in batches)
-        return (unsigned)k < (unsigned)st.W ? sp_ldg(st.sbits + (size_t)tile_puzzle[j] * st.W + k) : 0u;
+        return (unsigned)k < (unsigned)st.W ? sp_ldg(st.sbits + (tile_puzzle[j] * (uint32_t)st.W + (uint32_t)k)) : 0u;
     }
-    SPARC_HD uint32_t fix(int j, int k, uint32_t w) const {     // the shared-memory part
-        if ((unsigned)k >= (unsigned)st.W) return 0u;
+    SPARC_HD uint32_t fix(int j, int k, uint32_t w) const {     // the shared-memory part (k >= 0; words >= W stay 0)
         const uint32_t* row = dyn + j * SPARC_DYN_STRIDE;
-        if (k < st.nv) w |= row[k];
-        const uint32_t ab = row[8];
-        if ((int)(ab >> 5) == k) w |= 1u << (ab & 31);
-        return w;
+        const uint32_t v = (unsigned)k < (unsigned)st.nv ? row[k] : 0u;       // visited = plane 0
+        const uint32_t ab = row[8];                                           // agent bit (inside plane 2)
+        return w | v | ((int)(ab >> 5) == k ? 1u << (ab & 31) : 0u);
     }
     SPARC_HD uint32_t word(int j, int k) const { return fix(j, k, raw(j, k)); }
 };
@@ -755,7 +753,7 @@ struct ColorSrc {                       // colour plane, 4 bits per node
     SPARC_HD int L() const { return 4 * st.S; }
     SPARC_HD int W() const { return st.Wc; }
     SPARC_HD uint32_t raw(int j, int k) const {
-        return (unsigned)k < (unsigned)st.Wc ? sp_ldg(st.color4 + (size_t)tile_puzzle[j] * st.Wc + k) : 0u;
+        return (unsigned)k < (unsigned)st.Wc ? sp_ldg(st.color4 + (tile_puzzle[j] * (uint32_t)st.Wc + (uint32_t)k)) : 0u;
     }
     SPARC_HD uint32_t fix(int, int, uint32_t w) const { return w; }
     SPARC_HD uint32_t word(int j, int k) const { return raw(j, k); }
@@ -765,38 +763,34 @@ struct InfoNzSrc {                      // additional_info != 0, 1 bit per node
     SPARC_HD int L() const { return st.S; }
     SPARC_HD int W() const { return st.nv; }
     SPARC_HD uint32_t raw(int j, int k) const {
-        return (unsigned)k < (unsigned)st.nv ? sp_ldg(st.info_nz + (size_t)tile_puzzle[j] * st.nv + k) : 0u;
+        return (unsigned)k < (unsigned)st.nv ? sp_ldg(st.info_nz + (tile_puzzle[j] * (uint32_t)st.nv + (uint32_t)k)) : 0u;
     }
     SPARC_HD uint32_t fix(int, int, uint32_t w) const { return w; }
     SPARC_HD uint32_t word(int j, int k) const { return raw(j, k); }
 };
 
-// stage 1a (cooperative): rows[j][k] = env j's string shifted left by o_j, k in [0, W+1].
-// Four row words per thread per pass, all global loads issued before any is used.
+// stage 1a (cooperative): rows[j][k] = word k of env j's string, k in [0, W+1] (zeros behind the string).
+// Four row words per thread per pass, all global loads issued before any is used.  (Rows used to be stored
+// shifted by (j*L) mod 32 so that a chunk was one LDS + one shift; every row word then cost two loads, two
+// fix-ups and a funnel shift -- ~80 instructions, a quarter of k_encode<reference> and half of k_encode<compact>.
+// Plain rows cost ~20 per word and one more LDS + a funnel shift per fetch.)
 template <class Src>
 SPARC_HD void build_rows(const Src& src, uint32_t* rows, int nE, uint32_t inv_ws, int tid, int nthr) {
-    const int L = src.L(), Ws = src.W() + 2;
+    const int Ws = src.W() + 2;
     const int total = nE * Ws;
     for (int base = tid; base < total; base += 4 * nthr) {
         int j[4], k[4];
-        uint32_t o[4], hi[4], lo[4];
+        uint32_t w[4];
 #pragma unroll
         for (int u = 0; u < 4; u++) {
             const int idx = base + u * nthr;
             j[u] = (int)sp_umulhi((uint32_t)idx, inv_ws); k[u] = idx - j[u] * Ws;
-            o[u] = (uint32_t)(j[u] * L) & 31u;
-            const bool act = idx < total;
-            hi[u] = act ? src.raw(j[u], k[u]) : 0u;
-            lo[u] = (act && o[u]) ? src.raw(j[u], k[u] - 1) : 0u;
+            w[u] = idx < total ? src.raw(j[u], k[u]) : 0u;
         }
 #pragma unroll
         for (int u = 0; u < 4; u++) {
             const int idx = base + u * nthr;
-            if (idx < total) {
-                const uint32_t h = src.fix(j[u], k[u], hi[u]);
-                const uint32_t l = o[u] ? src.fix(j[u], k[u] - 1, lo[u]) : 0u;
-                rows[idx] = o[u] ? sp_funnel_r(l, h, 32u - o[u]) : h;   // (h << o) | (l >> (32 - o))
-            }
+            if (idx < total) rows[idx] = src.fix(j[u], k[u], w[u]);
         }
     }
 }
@@ -809,16 +803,20 @@ SPARC_HD void build_tails(const Src& src, uint32_t* rows, int nE, int A, int tid
         const int end = (j + 1) * L;                            // first stream bit of env j+1
         const int tb = (A - (end % A)) % A;
         if (!tb) continue;
-        const uint32_t bits = src.word(j + 1, 0) & ((1u << tb) - 1u);
-        const int pos = ((j * L) & 31) + L;                     // row-bit right behind env j's own bits
-        rows[j * Ws + (pos >> 5)] |= bits << (pos & 31);
+        const uint32_t bits = src.word(j + 1, 0) & (tb >= 32 ? 0xFFFFFFFFu : (1u << tb) - 1u);
+        uint32_t* r = rows + j * Ws + (L >> 5);                 // row-bit L: right behind env j's own bits
+        const int sh = L & 31;
+        r[0] |= bits << sh;
+        if (sh) r[1] |= bits >> (32 - sh);
     }
 }
-// stage 2 (cooperative): expand.  g = first stream bit of the chunk -> (env j, row bit)
+// stage 2 (cooperative): expand.  g = first stream bit of the chunk -> (env j, row bit); returns the 32 stream
+// bits from g on (bits behind the row's tail are zero / unspecified)
 SPARC_HD uint32_t row_fetch(const uint32_t* rows, uint32_t g, int L, int Ws, uint32_t inv_L) {
     const int j = (int)sp_umulhi(g, inv_L);
-    const uint32_t pos = (((uint32_t)(j * L)) & 31u) + (g - (uint32_t)(j * L));
-    return rows[j * Ws + (pos >> 5)] >> (pos & 31u);
+    const uint32_t pos = g - (uint32_t)(j * L);
+    const uint32_t* r = rows + j * Ws + (pos >> 5);
+    return sp_funnel_r(r[0], r[1], pos & 31u);
 }
 SPARC_HD void expand_base(const StoreDev& st, const uint32_t* rows, int32_t* out_tile, int nE, int tid, int nthr) {
     const int L = st.L, Ws = st.W + 2, total = nE * L, nchunks = total >> 2;
@@ -879,6 +877,9 @@ SPARC_HD uint32_t spread4(uint32_t nib) { return ((nib & 15u) * 0x00204081u) & 0
 // 4 nibbles (16 bits) -> 4 bytes
 SPARC_HD uint32_t nib4(uint32_t v) { return (v & 0xFu) | ((v & 0xF0u) << 4) | ((v & 0xF00u) << 8) | ((v & 0xF000u) << 12); }
 // planes: a 16-byte chunk = 16 elements = 16 stream bits
+// (A 256 x 8-byte shared-memory table -- stream byte -> 8 output bytes, two LDS.64 per chunk instead of the four
+// shift/mask/multiply/mask groups -- was measured slower: k_encode<compact> 59.7 -> 65.5 us; the loop is issue-bound
+// but the table's bank conflicts cost more than the ALU work they replace.)
 SPARC_HD void expand_base_u8(const StoreDev& st, const uint32_t* rows, uint8_t* out_tile, int nE, int tid, int nthr) {
     const int L = st.L, Ws = st.W + 2, total = nE * L, nchunks = total >> 4;
     for (int c = tid; c < nchunks; c += nthr) {
