@@ -691,7 +691,9 @@ static int launch_env(SparcEnv* e, KParams& p, void* stream) {
         const bool any_obs = p.obs.base_dev || p.obs.color_dev || p.obs.info_dev;
         const int nc = e->split_chunks;
         const int64_t per = ((n + nc - 1) / nc + 127) / 128 * 128;       // chunk boundaries stay 16-B aligned in every stream
-        p.tile = (compact && e->enc_tile < 32) ? 32 : e->enc_tile;     // compact: 32 envs = 81 KB per CTA (measured: 16 -> 0.090, 32 -> 0.078, 64 -> 0.077 ms)
+        // compact: 32 envs = 81 KB per CTA unless SPARC_ENC_TILE says otherwise (measured with plain-row staging,
+        // k_encode / step in us: 16 -> 59.7 / 86.7, 32 -> 59.8 / 82.3, 48 -> 62.6 / 83.8, 64 -> 67.9 / 87.2, 96 -> 80.7 / 95.5)
+        p.tile = compact ? ((getenv("SPARC_ENC_TILE") && e->enc_tile % 16 == 0) ? e->enc_tile : 32) : e->enc_tile;
         const size_t shmem = (size_t)(tile_head_words(p.tile) + tile_flat_words(p.st, p.tile)) * sizeof(uint32_t);
         cudaStream_t sd = nc > 1 ? e->side : s0;                         // one chunk: plain back-to-back launches
         const bool defer = p.mode == 0 && e->vq && e->cfg.validate_mode == SPARC_VALIDATE_TERMINAL;
@@ -729,6 +731,8 @@ static int launch_env(SparcEnv* e, KParams& p, void* stream) {
                 if (e->hostcopy.trunc) CU(cudaMemcpyAsync(e->hostcopy.trunc, e->trunc_stage, nn, cudaMemcpyDeviceToHost, e->copy_stream));
                 CU(cudaEventRecord(e->ev_copy, e->copy_stream));
             }
+            // (Launching k_val BEFORE k_encode -- so that its 124-register CTAs need not wait for encoder CTAs to retire
+            // from a full register file -- changed nothing: compact 0.0833 vs 0.0833 ms, reference 0.1861 vs 0.1850.)
             if (fork_val) {                                                  // k_val beside (the last) k_encode
                 if (nc == 1) CU(cudaStreamWaitEvent(e->side, e->ev_start, 0));
                 k_val<<<(unsigned)e->val_grid, CTA_THREADS, 0, e->side>>>(p);
