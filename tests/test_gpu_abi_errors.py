@@ -27,6 +27,9 @@ def test_bad_arguments_return_codes_and_messages():
     bad = abi.StoreDesc.from_buffer_copy(desc)
     bad.words_per_puzzle += 1
     assert lib.sparc_store_create(C.byref(bad), 0, C.byref(hs)) < 0
+    bad = abi.StoreDesc.from_buffer_copy(desc)
+    bad.n_puzzles = 2 ** 31 - 1                     # the encoder indexes the pool with 32-bit word offsets: refused up front
+    assert lib.sparc_store_create(C.byref(bad), 0, C.byref(hs)) < 0 and b"too large" in lib.sparc_last_error()
     assert lib.sparc_store_create(C.byref(desc), 0, C.byref(hs)) == 0
     assert lib.sparc_env_create(hs, 0, 0, 10, 0, 1, 1, C.byref(he)) < 0            # n_envs <= 0
     assert lib.sparc_env_create(hs, 8, 0, 10, 7, 1, 1, C.byref(he)) < 0            # autoreset mode
