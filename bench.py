@@ -180,6 +180,9 @@ def main():
     ap.add_argument("--no-extra", action="store_true", help="skip the short config-2 side measurement")
     ap.add_argument("--obs-format", default="reference", choices=["reference", "compact"],
                     help="reference = int32/int32/int64 planes (the reference's dtypes, the headline); compact = uint8/uint8/int32")
+    ap.add_argument("--obs-update", default="rewrite", choices=["rewrite", "delta"],
+                    help="rewrite = every step writes every observation in full (the headline); delta = the persistent "
+                         "observation is touched in place, full rewrite only for envs that begin a new episode")
     ap.add_argument("--no-graph", action="store_true", help="launch every step from Python instead of one CUDA graph of K steps")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
@@ -224,7 +227,7 @@ def main():
     # env-sharded: rank r owns global envs [r*n_env, (r+1)*n_env); global env i starts on puzzle i mod pool
     runner = ShardedRunner(rows, n_env * world, rank=rank, world=world, local_rank=local_rank, traceback=traceback,
                            max_steps=max_steps, autoreset_mode=args.autoreset, puzzle_stride=1, validate=args.validate,
-                           write_obs=not args.no_obs, obs_format=args.obs_format)
+                           write_obs=not args.no_obs, obs_format=args.obs_format, obs_update=args.obs_update)
     env = runner.env
     st = env.store
     t_build = time.perf_counter() - t_build
@@ -281,7 +284,7 @@ def main():
 
     # ---- the dominant kernel on its own: K launches of k_encode (state -> observation), CUDA events
     enc_ms = None
-    if not args.no_obs:
+    if not args.no_obs and args.obs_update == "rewrite":
         for _ in range(3):
             env.encode()
         barrier()
@@ -338,6 +341,12 @@ def main():
     if rank == 0:
         peak, peak_src = measured_peaks()
         b_alg = st.algorithmic_bytes_per_step(args.obs_format)
+        if args.obs_update == "delta":
+            # state + io + four touched plane elements + the full rewrites of the envs that began a new episode,
+            # amortised with the measured episode rate of this run
+            elem = 4 if args.obs_format == "reference" else 1
+            rate = stats["episodes"] / max(stats["steps"], 1)
+            b_alg = int(round(208 + 4 * elem + rate * (b_alg - 208)))
         value = n_env * world * K / (ms_max / 1e3)
         step_ms = ms_max / K
         fused = launches == K                      # small batches: the single fused kernel k_env is the step
@@ -355,8 +364,11 @@ def main():
                        "autoreset": args.autoreset, "validate": args.validate,
                        "launch": ("one CUDA graph of the K steps" if graph is not None else "K steps launched from Python")
                                  + f" ({launches // K} kernel launches per step)",
-                       "obs_mode": "full rewrite, reference dtypes" if args.obs_format == "reference" else
-                                   "full rewrite, COMPACT dtypes (uint8 planes, uint8 colour, int32 additional_info): own algorithmic bytes",
+                       "obs_mode": ("full rewrite" if args.obs_update == "rewrite" else
+                                    "DELTA: persistent observation touched in place, envs that begin a new episode rewritten in "
+                                    "full (own algorithmic bytes; latency-bound, not HBM-bound)") +
+                                   (", reference dtypes" if args.obs_format == "reference" else
+                                    ", COMPACT dtypes (uint8 planes, uint8 colour, int32 additional_info): own algorithmic bytes"),
                        "l2": ("observation written per step (%.0f MB) exceeds L2 (126 MB)" % (b_alg * n_env / 1e6))
                              if b_alg * n_env > 126e6 else
                              ("observation per step (%.1f MB) fits in L2: writes may be absorbed by L2" % (b_alg * n_env / 1e6)),
@@ -364,8 +376,10 @@ def main():
                        "ms_per_step_by_rank": [round(m / K, 5) for m in per_rank_ms]},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                         "frac": round(achieved / peak, 4), "traffic": ncu_traffic(args.workload, n_env) if args.obs_format == "reference" else None, "peak_source": peak_src,
-                         "kernel": "k_env (fused step)" if fused else "k_encode (state -> observation; the step = k_dyn, then k_val || k_encode)",
+                         "frac": round(achieved / peak, 4), "traffic": ncu_traffic(args.workload, n_env) if (args.obs_format == "reference" and args.obs_update == "rewrite") else None, "peak_source": peak_src,
+                         "kernel": "k_env (fused step)" if fused else
+                                   "the whole step = k_dyn (dynamics + in-place observation update), then k_val || k_encode_list" if args.obs_update == "delta" else
+                                   "k_encode (state -> observation; the step = k_dyn, then k_val || k_encode)",
                          "algorithmic_bytes_per_env_step": b_alg, "envs_per_launch": n_env,
                          "kernel_ms": round(kernel_ms, 5), "share_of_step": round(kernel_ms / step_ms, 4),
                          "whole_step": {"achieved": round(step_achieved, 1), "frac": round(step_achieved / peak, 4),
@@ -401,6 +415,21 @@ def main():
                     "roofline_frac_encoder": j3["roofline"]["frac"]}
             except Exception:
                 line["other_workloads"][args.workload + "_compact_obs"] = {"error": res.stderr[-200:]}
+            # the same workload with the observation updated in place (reference dtypes), under its OWN algorithmic bytes
+            res = subprocess.run([sys.executable, os.path.abspath(__file__), "--workload", args.workload, "--steps", "300",
+                                  "--warmup", "20", "--no-cpu-baseline", "--no-extra", "--no-e2e", "--obs-update", "delta"],
+                                 capture_output=True, text=True)
+            try:
+                j4 = json.loads(res.stdout.strip().splitlines()[-1])
+                line["other_workloads"][args.workload + "_delta_obs"] = {
+                    "description": "same envs and puzzles, the persistent observation touched in place (visited / agent_location "
+                                   "cells), envs that begin a new episode rewritten in full; same tensor contents after every step",
+                    "value": j4["value"], "unit": j4["unit"], "ms_per_step": j4["ms_per_step"],
+                    "algorithmic_bytes_per_env_step": j4["roofline"]["algorithmic_bytes_per_env_step"],
+                    "roofline_frac_whole_step": j4["roofline"]["whole_step"]["frac"],
+                    "note": "latency-bound (k_dyn, then the terminal validation k_val), not HBM-bound"}
+            except Exception:
+                line["other_workloads"][args.workload + "_delta_obs"] = {"error": res.stderr[-200:]}
         if not args.no_cpu_baseline and world == 1:
             # fresh interpreter: the worker pool must not be forked from a process holding a CUDA context
             res = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload",

@@ -153,7 +153,7 @@ typedef struct {                 /* all pointers are HOST pointers; copied by sp
 typedef struct SparcStore SparcStore;
 typedef struct SparcEnv SparcEnv;
 
-/* observation 'new' (SG.py:956-979), written in full every call.
+/* observation 'new' (SG.py:956-979), written in full every call (update = SPARC_OBS_REWRITE).
  * format SPARC_OBS_REFERENCE (0, the reference's dtypes -- the bit-exact drop-in and the headline benchmark):
  *   base  int32 [n_envs][n_planes][slab_x][slab_y]   (one-hot planes, SG.py:272-277, 305-306)
  *   color int32 [n_envs][slab_x][slab_y]             (SG.py:279)
@@ -163,12 +163,20 @@ typedef struct SparcEnv SparcEnv;
  *   base  uint8 [..], color uint8 [..], info int32 [..]   (same shapes)
  * contiguous, 16-byte aligned; any pointer may be NULL to skip that array. */
 enum { SPARC_OBS_REFERENCE = 0, SPARC_OBS_COMPACT = 1 };
+/* update SPARC_OBS_DELTA (sparc_step only): the arrays are the env's PERSISTENT observation, as in the reference,
+ * whose obs dict aliases the live planes and mutates them in place (SG.py:979, 1146-1188): a step touches only
+ * what changed -- visited / agent_location at the cell left and the cell entered -- and rewrites an env in full
+ * only when it starts a new episode (autoreset).  Same contents as a full rewrite after every call, provided the
+ * caller passes the same arrays every step and they hold the env's current observation (sparc_reset and
+ * sparc_encode always write in full).  A separate mode with its own algorithmic bytes, never mixed into the
+ * full-rewrite figures. */
+enum { SPARC_OBS_REWRITE = 0, SPARC_OBS_DELTA = 1 };
 typedef struct {
     void*   base_dev;
     void*   color_dev;
     void*   info_dev;
-    int32_t format;      /* SPARC_OBS_* */
-    int32_t reserved;    /* 0 */
+    int32_t format;      /* SPARC_OBS_REFERENCE / SPARC_OBS_COMPACT */
+    int32_t update;      /* SPARC_OBS_REWRITE / SPARC_OBS_DELTA */
 } SparcObsOut;
 
 /* per-env step results (SG.py:1238); any pointer may be NULL */

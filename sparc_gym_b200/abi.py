@@ -51,12 +51,13 @@ class StoreDesc(C.Structure):
                 ("shapes", C.c_void_p), ("trie", C.c_void_p)]
 
 
+OBS_UPDATES = {"rewrite": 0, "delta": 1}         # SPARC_OBS_REWRITE (full rewrite every call) | SPARC_OBS_DELTA (in place)
 OBS_FORMATS = {"reference": 0, "compact": 1}     # SPARC_OBS_*: int32/int32/int64 (the reference's dtypes) | uint8/uint8/int32
 
 
 class ObsOut(C.Structure):
     _fields_ = [("base_dev", C.c_void_p), ("color_dev", C.c_void_p), ("info_dev", C.c_void_p),
-                ("format", C.c_int32), ("reserved", C.c_int32)]
+                ("format", C.c_int32), ("update", C.c_int32)]
 
 
 class StepOut(C.Structure):

@@ -55,6 +55,8 @@ struct SparcEnv {
     struct { float* reward; uint8_t* term; uint8_t* trunc; bool active; } hostcopy;
     uint32_t* vq_count;      // deferred-validation queue (split path, validate = terminal)
     uint32_t* vq;
+    uint32_t* rq_count;      // update = SPARC_OBS_DELTA: envs that began a new episode this step (count, finished CTAs)
+    uint32_t* rq;            // [n_envs]
     int val_grid;
     int ring_grid;           // >0: use k_env_ring with this many persistent CTAs (one per SM)
     unsigned int* sched;     // [2] tile counter + finished-producer counter of k_env_ring
@@ -120,14 +122,21 @@ __global__ void __launch_bounds__(CTA_THREADS, SPARC_MINBLOCKS) k_env(const KPar
     EnvRegs e;
     unsigned long long my_stats[SPARC_N_STATS];
     bool have_stats = false;
+    bool full = false;
     if (tid < nE) {
-        have_stats = phase_a(p, env0 + tid, e, head + tid * SPARC_DYN_STRIDE, my_stats);
+        have_stats = phase_a(p, env0 + tid, e, head + tid * SPARC_DYN_STRIDE, my_stats, &full);
         head[p.tile * SPARC_DYN_STRIDE + tid] = e.puzzle;
         write_dyn(st, head, tid, e);
     }
     if (p.mode == 0 && tid < ((nE + 31) & ~31)) reduce_stats(p, have_stats, my_stats);
     if (!p.obs.base_dev && !p.obs.color_dev && !p.obs.info_dev) return;
-    __syncthreads();
+    if (p.mode == 0 && p.obs.update == SPARC_OBS_DELTA) {
+        // persistent observation: phase A has touched the cells that changed; the tile is rewritten only when one
+        // of its envs began a new episode (the others' in-place writes carry the same values)
+        if (!__syncthreads_or(full)) return;
+    } else {
+        __syncthreads();
+    }
     encode_tile_stage1a(st, head, flats, p.tile, nE, p.obs, tid, CTA_THREADS);
     __syncthreads();
     encode_tile_stage1b<FMT>(st, head, flats, p.tile, nE, p.obs, tid, CTA_THREADS);
@@ -151,14 +160,14 @@ __global__ void __launch_bounds__(CTA_THREADS, SPARC_MINBLOCKS) k_env(const KPar
 // the CUDA graph of bench.py: 0.196 -> 0.202 ms/step at 131,072 envs, 0.108 -> 0.117 at 65,536, 0.044 -> 0.051 at
 // 16,384.  The parked encoder CTAs take registers and issue slots from the latency-bound dynamics; the graph's
 // kernel-to-kernel edge is already ~1 us.  Removed.)
-template <bool INLINE_VALIDATION>
+template <bool INLINE_VALIDATION, bool DELTA>
 __global__ void __launch_bounds__(CTA_THREADS, DYN_MINBLOCKS) k_dyn(const KParams p, long long lo, long long hi) {
     const long long i = lo + (long long)blockIdx.x * CTA_THREADS + threadIdx.x;
     EnvRegs e;
     unsigned long long my_stats[SPARC_N_STATS];
     uint32_t scratch[SPARC_DYN_STRIDE];
     bool have_stats = false;
-    if (i < hi) have_stats = phase_a<INLINE_VALIDATION>(p, i, e, scratch, my_stats);
+    if (i < hi) have_stats = phase_a<INLINE_VALIDATION, DELTA>(p, i, e, scratch, my_stats);
     if (p.mode == 0) reduce_stats(p, have_stats, my_stats);
 }
 
@@ -223,6 +232,36 @@ __global__ void __launch_bounds__(ENC_THREADS, ENC_MINBLOCKS) k_encode(const KPa
     __syncthreads();
 #endif
     encode_tile_stage2<FMT>(st, head, flats, p.tile, nE, env0, p.obs, tid, ENC_THREADS);
+}
+
+// update = SPARC_OBS_DELTA on the split path: k_dyn touches the changed cells in place and queues the envs that began a
+// new episode (1-2 % per step); this kernel rewrites those in full, one env per CTA pass, and leaves the queue empty.
+template <int FMT>
+__global__ void __launch_bounds__(ENC_THREADS) k_encode_list(const KParams p) {
+    const StoreDev& st = p.st;
+    const int tid = threadIdx.x;
+    const uint32_t count = *p.rq_count;
+    uint32_t* head = smem;
+    uint32_t* flats = smem + tile_head_words(1);
+    for (uint32_t slot = blockIdx.x; slot < count; slot += gridDim.x) {
+        const long long env = (long long)p.rq[slot];
+        if (tid == 0) {
+            EnvRegs e;
+            load_env(e, p.sd, st, p.cfg.n_envs, env);
+            head[SPARC_DYN_STRIDE] = e.puzzle;
+            write_dyn(st, head, 0, e);
+        }
+        __syncthreads();
+        encode_tile_stage1a(st, head, flats, 1, 1, p.obs, tid, ENC_THREADS);
+        __syncthreads();
+        encode_env_elementwise<FMT>(st, head, flats, env, p.obs, tid, ENC_THREADS);
+        __syncthreads();                                         // the rows are reused by the next pass
+    }
+    __syncthreads();                                             // every thread of the CTA has read `count`
+    if (tid == 0) {                                              // last CTA out empties the queue for the next step
+        __threadfence();
+        if (atomicAdd(p.rq_count + 1, 1u) == gridDim.x - 1) { p.rq_count[0] = 0; p.rq_count[1] = 0; }
+    }
 }
 
 // ---- ring kernel: one persistent, warp-specialised CTA per SM -------------------------------------
@@ -649,6 +688,8 @@ int sparc_env_create(SparcStore* store, int64_t n_envs, int traceback, int max_s
     if (traceback) alloc((void**)&e->s.moves, n * SPARC_MOVE_WORDS * 4);
     alloc((void**)&e->s.stats, (size_t)SPARC_STAT_ROWS * SPARC_N_STATS * 8);
     alloc((void**)&e->sched, 16 * sizeof(unsigned int));   // [2..] cycle counters when built with -DRING_PROFILE
+    alloc((void**)&e->rq_count, 2 * sizeof(uint32_t));
+    alloc((void**)&e->rq, n * sizeof(uint32_t));
     alloc((void**)&e->act_stage, n);
     alloc((void**)&e->rew_stage, n * 4);
     alloc((void**)&e->term_stage, n);
@@ -664,7 +705,7 @@ int sparc_env_create(SparcStore* store, int64_t n_envs, int traceback, int max_s
 int sparc_env_destroy(SparcEnv* e) {
     if (!e) return SPARC_OK;
     cudaSetDevice(e->store->device);
-    void* ptrs[] = {e->s.core, e->s.vis, e->s.ep_ret, e->s.moves, e->s.stats, e->sched, e->vq_count, e->vq, e->act_stage, e->rew_stage, e->term_stage, e->trunc_stage};
+    void* ptrs[] = {e->s.core, e->s.vis, e->s.ep_ret, e->s.moves, e->s.stats, e->sched, e->vq_count, e->vq, e->rq_count, e->rq, e->act_stage, e->rew_stage, e->term_stage, e->trunc_stage};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (e->side) cudaStreamDestroy(e->side);
     if (e->ev_start) cudaEventDestroy(e->ev_start);
@@ -685,6 +726,8 @@ static int launch_env(SparcEnv* e, KParams& p, void* stream) {
     const bool compact = p.obs.format == SPARC_OBS_COMPACT;
     if (compact && p.tile < 16) p.tile = 16;
     const unsigned ntiles = (unsigned)((n + p.tile - 1) / p.tile);
+    if (p.obs.update != SPARC_OBS_REWRITE && p.obs.update != SPARC_OBS_DELTA) return fail(SPARC_E_ARG, "bad observation update mode%s");
+    if (p.mode == 1) p.obs.update = SPARC_OBS_REWRITE;                   // a reset always writes in full
     if (e->split_chunks > 0) {
         // chunk c: [k_dyn on the side stream] -> event -> [k_encode on the caller's stream]
         cudaStream_t s0 = (cudaStream_t)stream;
@@ -697,6 +740,8 @@ static int launch_env(SparcEnv* e, KParams& p, void* stream) {
         const size_t shmem = (size_t)(tile_head_words(p.tile) + tile_flat_words(p.st, p.tile)) * sizeof(uint32_t);
         cudaStream_t sd = nc > 1 ? e->side : s0;                         // one chunk: plain back-to-back launches
         const bool defer = p.mode == 0 && e->vq && e->cfg.validate_mode == SPARC_VALIDATE_TERMINAL;
+        const bool delta = any_obs && p.obs.update == SPARC_OBS_DELTA;
+        if (delta) { p.rq = e->rq; p.rq_count = e->rq_count; }          // (k_encode_list leaves the queue empty)
         if (defer) {
             p.vq = e->vq; p.vq_count = e->vq_count;                     // (k_val leaves the queue empty)
         }
@@ -708,8 +753,8 @@ static int launch_env(SparcEnv* e, KParams& p, void* stream) {
             const long long lo = (long long)c * per, hi = lo + per < n ? lo + per : n;
             if (lo >= hi) break;
             const unsigned dgrid = (unsigned)((hi - lo + CTA_THREADS - 1) / CTA_THREADS);
-            if (defer) k_dyn<false><<<dgrid, CTA_THREADS, 0, sd>>>(p, lo, hi);
-            else k_dyn<true><<<dgrid, CTA_THREADS, 0, sd>>>(p, lo, hi);
+            if (defer) { if (delta) k_dyn<false, true><<<dgrid, CTA_THREADS, 0, sd>>>(p, lo, hi); else k_dyn<false, false><<<dgrid, CTA_THREADS, 0, sd>>>(p, lo, hi); }
+            else { if (delta) k_dyn<true, true><<<dgrid, CTA_THREADS, 0, sd>>>(p, lo, hi); else k_dyn<true, false><<<dgrid, CTA_THREADS, 0, sd>>>(p, lo, hi); }
             if (nc > 1) {
                 CU(cudaEventRecord(e->ev_dyn[c], e->side));
                 CU(cudaStreamWaitEvent(s0, e->ev_dyn[c], 0));
@@ -718,7 +763,17 @@ static int launch_env(SparcEnv* e, KParams& p, void* stream) {
             const bool fork_val = defer && last;
             const bool fork_copy = e->hostcopy.active && nc == 1;
             if (nc == 1 && (fork_val || fork_copy)) CU(cudaEventRecord(e->ev_start, s0));   // = k_dyn done
-            if (any_obs) {
+            if (delta) {
+                if (last) {                                                  // the envs that began a new episode, in full
+                    const size_t shmem1 = (size_t)(tile_head_words(1) + tile_flat_words(p.st, 1)) * sizeof(uint32_t);
+                    // ~1.6 % of the envs end an episode per step under random play: one queue entry per CTA pass when the
+                    // grid covers n / 32 entries (CTAs beyond the queue length leave at once)
+                    const int64_t want = (n + 31) / 32;
+                    const unsigned lgrid = (unsigned)(want < 148 ? (n < 148 ? n : 148) : (want > 148 * 32 ? 148 * 32 : want));
+                    if (compact) k_encode_list<SPARC_OBS_COMPACT><<<lgrid, ENC_THREADS, shmem1, s0>>>(p);
+                    else k_encode_list<SPARC_OBS_REFERENCE><<<lgrid, ENC_THREADS, shmem1, s0>>>(p);
+                }
+            } else if (any_obs) {
                 const unsigned egrid = (unsigned)((hi - lo + p.tile - 1) / p.tile);
                 if (compact) k_encode<SPARC_OBS_COMPACT><<<egrid, ENC_THREADS, shmem, s0>>>(p, lo, hi);
                 else k_encode<SPARC_OBS_REFERENCE><<<egrid, ENC_THREADS, shmem, s0>>>(p, lo, hi);
@@ -741,12 +796,13 @@ static int launch_env(SparcEnv* e, KParams& p, void* stream) {
                 CU(cudaStreamWaitEvent(s0, e->ev_val, 0));                   // join
             }
             if (fork_copy) CU(cudaStreamWaitEvent(s0, e->ev_copy, 0));
-            e->launches += any_obs ? 2 : 1;
+            e->launches += (delta ? last : any_obs) ? 2 : 1;
         }
         CU(cudaGetLastError());
         return SPARC_OK;
     }
     if (e->ring_grid > 0) {
+        if (p.obs.update == SPARC_OBS_DELTA) return fail(SPARC_E_ARG, "the ring kernel (SPARC_RING=1) rewrites the observation in full only%s");
         if (compact) return fail(SPARC_E_ARG, "the ring kernel (SPARC_RING=1) writes the reference format only%s");
         p.tile = RING_TILE;
         const size_t shmem = (size_t)(4 * RING_PROD + RING_PROD * ring_slot_words(p.st) + RING_CONS * 2 * STAGE_WORDS) * sizeof(uint32_t);

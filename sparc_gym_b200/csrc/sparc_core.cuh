@@ -926,6 +926,9 @@ SPARC_HD void expand_info_i32(const StoreDev& st, const uint32_t* rows, const ui
     }
 }
 
+template <int FMT> struct ObsTypes { typedef int32_t base_t; typedef int64_t info_t; };          // SPARC_OBS_REFERENCE
+template <> struct ObsTypes<SPARC_OBS_COMPACT> { typedef uint8_t base_t; typedef int32_t info_t; };
+
 // shared-memory words: per-tile header (dyn rows + puzzle ids) and the three row sets
 SPARC_HD int tile_head_words(int tile) { return tile * (SPARC_DYN_STRIDE + 1); }
 SPARC_HD int tile_flat_words(const StoreDev& st, int tile) { return tile * ((st.W + 2) + (st.Wc + 2) + (st.nv + 2)); }
@@ -977,6 +980,35 @@ SPARC_HD void encode_tile_stage2(const StoreDev& st, const uint32_t* head, const
     if (obs.info_dev) expand_info(st, rz, tile_puzzle, static_cast<int64_t*>(obs.info_dev) + (size_t)env0 * st.S, nE, tid, nthr);
 }
 
+// One env's whole observation from rows staged with tile = 1 (k_encode_list: the few envs per step that began a
+// new episode under update = SPARC_OBS_DELTA).  Element-wise stores, consecutive threads -> consecutive elements:
+// an env's streams start at 8- or 4-byte boundaries only (L*4 = 6,760 bytes on the 13x13 / 10-plane slab).
+template <int FMT>
+SPARC_HD void encode_env_elementwise(const StoreDev& st, const uint32_t* head, const uint32_t* flats, long long env,
+                                     const SparcObsOut& obs, int tid, int nthr) {
+    typedef typename ObsTypes<FMT>::base_t base_t;
+    typedef typename ObsTypes<FMT>::info_t info_t;
+    const uint32_t puzzle = head[SPARC_DYN_STRIDE];
+    const uint32_t* rb = flats;
+    const uint32_t* rc = rb + (st.W + 2);
+    const uint32_t* rz = rc + (st.Wc + 2);
+    if (obs.base_dev) {
+        base_t* out = static_cast<base_t*>(obs.base_dev) + (size_t)env * st.L;
+        for (int e = tid; e < st.L; e += nthr) out[e] = (base_t)(row_fetch(rb, (uint32_t)e, st.L, st.W + 2, st.inv_L) & 1u);
+    }
+    if (obs.color_dev) {
+        base_t* out = static_cast<base_t*>(obs.color_dev) + (size_t)env * st.S;
+        for (int e = tid; e < st.S; e += nthr) out[e] = (base_t)(row_fetch(rc, 4u * (uint32_t)e, 4 * st.S, st.Wc + 2, st.inv_4S) & 15u);
+    }
+    if (obs.info_dev) {
+        info_t* out = static_cast<info_t*>(obs.info_dev) + (size_t)env * st.S;
+        for (int e = tid; e < st.S; e += nthr) {
+            const uint32_t m = row_fetch(rz, (uint32_t)e, st.S, st.nv + 2, st.inv_S) & 1u;
+            out[e] = m ? (info_t)sp_ldg(st.info + (size_t)puzzle * st.S + e) : (info_t)0;
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // one launch = reset or step of all envs (+ observation rewrite)
 // ---------------------------------------------------------------------------------------------
@@ -994,6 +1026,8 @@ struct KParams {
     SparcObsOut obs;
     uint32_t* vq_count;      // deferred terminal validation: number of queued envs (nullptr = validate inline)
     uint32_t* vq;            // [n_envs][SPARC_VQ_WORDS]: env, puzzle, x | y << 8, pad, visited[8]
+    uint32_t* rq_count;      // delta observations: number of envs that began a new episode this step (nullptr in the
+    uint32_t* rq;            // fused kernel, which decides per tile); [n_envs] their indices -> k_encode_list
 };
 #define SPARC_VQ_WORDS 12
 
@@ -1011,14 +1045,32 @@ SPARC_HD float reward_value(int code) {
 // Phase A for env i (one thread): reset / autoreset / frozen / live step, terminal validation,
 // per-env outputs.  `scratch` = 9 words the validator may use.  Returns true when `stats`
 // (SPARC_N_STATS counters) were filled.  On exit `e` is the state the observation must show.
-template <bool INLINE_VALIDATION = true>
-SPARC_HD bool phase_a(const KParams& p, long long i, EnvRegs& e, uint32_t* scratch, unsigned long long* stats) {
+// In-place observation update of one env after a move (update = SPARC_OBS_DELTA; SG.py:1146-1188 mutates the aliased
+// planes the same way): agent_location leaves (ox, oy) and enters (x, y); visited is set at (x, y) and, at (ox, oy),
+// keeps its value after a fresh move or is cleared by a traceback undo -- i.e. it becomes the state's bit.
+template <typename T>
+SPARC_HD void obs_delta_planes(T* base, const StoreDev& st, long long i, int ox, int oy, const EnvRegs& e) {
+    T* b = base + (size_t)i * st.L;
+    const int o = ox * st.SY + oy, c = e.x * st.SY + e.y;
+    b[o] = (T)board_bit(e.v, o);                 // plane 0: visited
+    b[c] = (T)1;
+    b[2 * st.S + o] = (T)0;                      // plane 2: agent_location
+    b[2 * st.S + c] = (T)1;
+}
+
+// `full` (optional): set when the env began a new episode in this call, i.e. its whole observation changed.
+// MAY_DELTA = false compiles the in-place observation update out (k_dyn of the full-rewrite step: 62 registers
+// instead of 66, i.e. 8 instead of 7 resident CTAs per SM).
+template <bool INLINE_VALIDATION = true, bool MAY_DELTA = true>
+SPARC_HD bool phase_a(const KParams& p, long long i, EnvRegs& e, uint32_t* scratch, unsigned long long* stats,
+                      bool* full = nullptr) {
     const StoreDev& st = p.st;
     const long long n = p.cfg.n_envs;
     load_env(e, p.sd, st, n, i);
     StepResult r;
     r.reward_code = SPARC_R_ZERO; r.terminated = 0; r.truncated = 0; r.legal_mask = 0; r.rule_flags = 0;
-    bool need_legal = false, have_stats = false;
+    bool need_legal = false, have_stats = false, new_episode = false;
+    const int ox = (int)e.x, oy = (int)e.y;
     if (p.mode == 1) {                                                   // ---- reset (SG.py:1057-1108)
         const bool sel = p.reset_mask ? p.reset_mask[i] != 0 : true;
         if (sel) {
@@ -1026,6 +1078,7 @@ SPARC_HD bool phase_a(const KParams& p, long long i, EnvRegs& e, uint32_t* scrat
             if (pz >= (uint32_t)st.n_puzzles) pz %= (uint32_t)st.n_puzzles;
             env_reset(e, st, pz);
             store_env(e, p.sd, st, n, i);
+            new_episode = true;
         }
         need_legal = true;
         r.terminated = (e.flags & FL_TERM) != 0; r.truncated = (e.flags & FL_TRUNC) != 0;
@@ -1033,6 +1086,7 @@ SPARC_HD bool phase_a(const KParams& p, long long i, EnvRegs& e, uint32_t* scrat
         if (p.cfg.autoreset == SPARC_AUTORESET_NEXT_STEP) {
             env_reset(e, st, (e.puzzle + (uint32_t)p.cfg.stride) % (uint32_t)st.n_puzzles);
             store_env(e, p.sd, st, n, i);
+            new_episode = true;
         } else {                                                         // frozen until sparc_reset
             r.terminated = (e.flags & FL_TERM) != 0; r.truncated = (e.flags & FL_TRUNC) != 0;
         }
@@ -1078,6 +1132,7 @@ SPARC_HD bool phase_a(const KParams& p, long long i, EnvRegs& e, uint32_t* scrat
             if (p.cfg.autoreset == SPARC_AUTORESET_SAME_STEP) {
                 env_reset(e, st, (e.puzzle + (uint32_t)p.cfg.stride) % (uint32_t)st.n_puzzles);
                 need_legal = true;
+                new_episode = true;
             } else {
                 e.flags = FL_DONE | (r.terminated ? FL_TERM : 0) | (r.truncated ? FL_TRUNC : 0);
             }
@@ -1085,6 +1140,22 @@ SPARC_HD bool phase_a(const KParams& p, long long i, EnvRegs& e, uint32_t* scrat
         store_env(e, p.sd, st, n, i);
     }
     if (need_legal) r.legal_mask = env_legal_now(e, st, p.sd, p.cfg, i);
+    if (full) *full = new_episode;
+    if (MAY_DELTA && p.mode == 0 && p.obs.update == SPARC_OBS_DELTA) {   // persistent observation, touched in place
+        if (new_episode) {
+            if (p.rq_count) {                                            // whole observation: k_encode_list rewrites it
+#if defined(__CUDA_ARCH__)
+                const uint32_t slot = atomicAdd(p.rq_count, 1u);
+#else
+                const uint32_t slot = (*p.rq_count)++;
+#endif
+                p.rq[slot] = (uint32_t)i;
+            }
+        } else if (p.obs.base_dev && ((int)e.x != ox || (int)e.y != oy)) {
+            if (p.obs.format == SPARC_OBS_COMPACT) obs_delta_planes(static_cast<uint8_t*>(p.obs.base_dev), st, i, ox, oy, e);
+            else obs_delta_planes(static_cast<int32_t*>(p.obs.base_dev), st, i, ox, oy, e);
+        }
+    }
     // per-env outputs (SG.py:1238)
     if (p.out.reward_dev) p.out.reward_dev[i] = reward_value(r.reward_code);
     if (p.out.reward_code_dev) p.out.reward_code_dev[i] = (int8_t)r.reward_code;

@@ -66,11 +66,15 @@ class SparcVecEnv:
                    (SG.py:941-950) runs inside step(); its flags land in info['rule_flags']
     obs_format     'reference' (int32 planes, int32 colour, int64 additional_info: the reference's dtypes,
                    SG.py:272-280) or 'compact' (uint8 / uint8 / int32: same values, 3.5x fewer bytes)
+    obs_update     'rewrite' (every step writes every observation in full) or 'delta': `self.obs` is the envs'
+                   persistent observation, as the reference's aliased planes are (SG.py:979, 1146-1188) -- a step
+                   touches the visited / agent_location cells that changed and rewrites an env in full only when it
+                   starts a new episode.  Same tensors, same contents after every call; do not write into them.
     """
 
     def __init__(self, puzzles, num_envs, traceback=False, max_steps=2000, autoreset_mode="next_step",
                  puzzle_stride=1, validate="terminal", device="cuda:0", slab=None, planes="auto",
-                 write_obs=True, obs_format="reference"):
+                 write_obs=True, obs_format="reference", obs_update="rewrite"):
         self.store = _as_store(puzzles, slab=slab, planes=planes) if not isinstance(puzzles, DeviceStore) else puzzles.host
         self.dstore = puzzles if isinstance(puzzles, DeviceStore) else DeviceStore(self.store, device)
         self.device = self.dstore.device
@@ -103,7 +107,9 @@ class SparcVecEnv:
         self.agent_xy = torch.zeros((N, 2), dtype=torch.uint8, device=dev)
         self._stats = torch.zeros(abi.N_STATS, dtype=torch.int64, device=dev)
         self._obs_out = abi.ObsOut(self.obs["base"].data_ptr(), self.obs["color"].data_ptr(),
-                                   self.obs["additional_info"].data_ptr(), abi.OBS_FORMATS[obs_format], 0)
+                                   self.obs["additional_info"].data_ptr(), abi.OBS_FORMATS[obs_format],
+                                   abi.OBS_UPDATES[obs_update])
+        self.obs_update = obs_update
         self._no_obs = abi.ObsOut(None, None, None, 0, 0)
         self._step_out = abi.StepOut(self.reward.data_ptr(), self.reward_code.data_ptr(),
                                      self.terminated.data_ptr(), self.truncated.data_ptr(),
@@ -205,6 +211,8 @@ class SparcVecEnv:
             raise ValueError("state blob does not match this env")
         with torch.cuda.device(self.device):
             abi.check(self.lib.sparc_state_load(self.handle, blob.data_ptr(), self._stream()))
+        if self.obs_update == "delta" and self.write_obs:
+            self.encode()                 # the persistent observation must show the restored state
 
     @property
     def kernel_launches(self):

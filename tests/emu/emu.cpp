@@ -46,6 +46,14 @@ int emu_launch(const SparcStoreDesc* desc, uint32_t* core, uint32_t* vis, int32_
     std::vector<uint32_t> vq;
     uint32_t vq_count = 0;
     if (defer_validation) { vq.resize((size_t)n_envs * SPARC_VQ_WORDS); p.vq = vq.data(); p.vq_count = &vq_count; }
+    // update = SPARC_OBS_DELTA: with defer_validation (the split step: k_dyn, then k_val || k_encode_list) the envs that
+    // began a new episode are queued and rewritten one by one; otherwise (the fused k_env) a tile is rewritten when
+    // one of its envs did
+    const bool delta = mode == 0 && p.obs.update == SPARC_OBS_DELTA;
+    if (mode == 1) p.obs.update = SPARC_OBS_REWRITE;
+    std::vector<uint32_t> rq;
+    uint32_t rq_count = 0;
+    if (delta && defer_validation) { rq.resize((size_t)n_envs); p.rq = rq.data(); p.rq_count = &rq_count; }
     const StoreDev& st = p.st;
     // exactly the dynamic shared memory the kernels request: an out-of-bounds row access is an ASan error
     std::vector<uint32_t> smem((size_t)tile_head_words(tile) + tile_flat_words(st, tile), 0xDEADBEEFu);
@@ -54,13 +62,17 @@ int emu_launch(const SparcStoreDesc* desc, uint32_t* core, uint32_t* vis, int32_
         const int nE = (int)((n_envs - env0) < tile ? (n_envs - env0) : tile);
         uint32_t* dyn = smem.data();
         uint32_t* tile_puzzle = dyn + (size_t)tile * SPARC_DYN_STRIDE;
+        bool any_full = false;
         for (int tid = 0; tid < nE; tid++) {
             unsigned long long my[SPARC_N_STATS];
-            if (phase_a(p, env0 + tid, regs[tid], dyn + tid * SPARC_DYN_STRIDE, my) && mode == 0)
+            bool full = false;
+            if (phase_a(p, env0 + tid, regs[tid], dyn + tid * SPARC_DYN_STRIDE, my, &full) && mode == 0)
                 for (int k = 0; k < SPARC_N_STATS; k++) stats[k] += my[k];
+            any_full |= full;
             tile_puzzle[tid] = regs[tid].puzzle;
             write_dyn(st, dyn, tid, regs[tid]);
         }
+        if (delta && (defer_validation || !any_full)) continue;
         uint32_t* flats = dyn + tile_head_words(tile);
         for (int tid = 0; tid < nthr; tid++) encode_tile_stage1a(st, dyn, flats, tile, nE, p.obs, tid, nthr);
         if (p.obs.format == SPARC_OBS_COMPACT) {
@@ -72,6 +84,23 @@ int emu_launch(const SparcStoreDesc* desc, uint32_t* core, uint32_t* vis, int32_
         }
     }
     for (uint32_t slot = 0; slot < vq_count; slot++) stats[SPARC_STAT_RULES_PASS] += validate_queued(p, slot);
+    if (delta && defer_validation) {                                  // k_encode_list
+        std::vector<uint32_t> sm1((size_t)tile_head_words(1) + tile_flat_words(st, 1), 0xDEADBEEFu);
+        uint32_t* head = sm1.data();
+        uint32_t* flats = head + tile_head_words(1);
+        for (uint32_t slot = 0; slot < rq_count; slot++) {
+            const long long env = rq[slot];
+            EnvRegs e;
+            load_env(e, p.sd, st, n_envs, env);
+            head[SPARC_DYN_STRIDE] = e.puzzle;
+            write_dyn(st, head, 0, e);
+            for (int tid = 0; tid < nthr; tid++) encode_tile_stage1a(st, head, flats, 1, 1, p.obs, tid, nthr);
+            for (int tid = 0; tid < nthr; tid++) {
+                if (p.obs.format == SPARC_OBS_COMPACT) encode_env_elementwise<SPARC_OBS_COMPACT>(st, head, flats, env, p.obs, tid, nthr);
+                else encode_env_elementwise<SPARC_OBS_REFERENCE>(st, head, flats, env, p.obs, tid, nthr);
+            }
+        }
+    }
     return 0;
 }
 

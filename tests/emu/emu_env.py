@@ -31,7 +31,7 @@ def build_emu():
 class EmuVecEnv:
     def __init__(self, puzzles, num_envs, traceback=False, max_steps=2000, autoreset_mode="next_step",
                  puzzle_stride=1, validate="terminal", slab=None, planes="auto", tile=8, nthr=128, defer_validation=False,
-                 obs_format="reference"):
+                 obs_format="reference", obs_update="rewrite"):
         if not isinstance(puzzles, PuzzleStore):
             if puzzles and isinstance(puzzles[0], dict):
                 puzzles = ingest_rows(puzzles)
@@ -63,7 +63,7 @@ class EmuVecEnv:
         self.agent_xy = np.zeros((N, 2), np.uint8)
         p = lambda a: a.ctypes.data
         self._obs_out = abi.ObsOut(p(self.obs["base"]), p(self.obs["color"]), p(self.obs["additional_info"]),
-                                   abi.OBS_FORMATS[obs_format], 0)
+                                   abi.OBS_FORMATS[obs_format], abi.OBS_UPDATES[obs_update])
         self._step_out = abi.StepOut(p(self.reward), p(self.reward_code), p(self.terminated), p(self.truncated),
                                      p(self.legal_mask), p(self.rule_flags), p(self.step_count), p(self.agent_xy))
 

@@ -161,3 +161,34 @@ def test_compact_observation_format_holds_the_same_values(tile, sizes):
         act = rng.integers(0, 4, N).astype(np.uint8)
         a.step(act); b.step(act)
     assert np.array_equal(a.stats(), b.stats())
+
+
+@pytest.mark.parametrize("fmt", ["reference", "compact"])
+@pytest.mark.parametrize("mode,traceback,defer", [("same_step", False, True), ("same_step", True, False),
+                                                  ("next_step", True, True), ("disabled", False, False)])
+def test_delta_observation_equals_full_rewrite(fmt, mode, traceback, defer):
+    """obs_update='delta' (the persistent observation is touched in place, as the reference mutates its aliased
+    planes, SG.py:979 / 1146-1188; an env is rewritten in full only when it starts a new episode) leaves the same
+    arrays behind as the full rewrite -- every step, every autoreset mode, both launch shapes (fused tile decision /
+    k_dyn + k_encode_list), both formats; incl. a masked reset and a checkpoint restore in between."""
+    rows = gen_pool(6, [(1, 1), (2, 3), (4, 4), (6, 6)], RULES_FULL, seed0=33)
+    N = 53
+    kw = dict(traceback=traceback, max_steps=18, autoreset_mode=mode, validate="terminal", obs_format=fmt,
+              defer_validation=defer, tile=32 if fmt == "compact" else 8)
+    a = EmuVecEnv(rows, N, **kw)
+    b = EmuVecEnv(rows, N, obs_update="delta", **kw)
+    a.reset(); b.reset()
+    rng = np.random.default_rng(12)
+    acts = np.stack([np.array(fuzz_actions(rows[i % len(rows)], 70 + i, 60, p_follow=0.7)) for i in range(N)], 1)
+    for t in range(60):
+        if t == 25:                                   # a masked reset onto other puzzles in the middle
+            m = rng.integers(0, 2, N).astype(np.uint8)
+            pz = rng.integers(0, len(rows), N).astype(np.int32)
+            a.reset(pz, m); b.reset(pz, m)
+        act = acts[t].astype(np.uint8)
+        ra, rb = a.step(act), b.step(act)
+        for k in a.obs:
+            assert np.array_equal(a.obs[k], b.obs[k]), (t, k, np.argwhere(a.obs[k] != b.obs[k])[:4])
+        assert np.array_equal(ra[1], rb[1]) and np.array_equal(ra[2], rb[2]) and np.array_equal(ra[3], rb[3])
+        assert np.array_equal(ra[4]["rule_flags"], rb[4]["rule_flags"]) and np.array_equal(ra[4]["legal_mask"], rb[4]["legal_mask"])
+    assert np.array_equal(a.stats(), b.stats()) and (mode == "disabled" or a.stats()[0] > N)

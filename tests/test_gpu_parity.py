@@ -244,3 +244,34 @@ def test_compact_observation_format_on_the_gpu(n_envs):
     for k in snap:
         assert torch.equal(snap[k], b.obs[k]), k
     assert torch.equal(a.stats(), b.stats())
+
+
+@pytest.mark.parametrize("fmt", ["reference", "compact"])
+@pytest.mark.parametrize("n_envs,mode", [(70, "next_step"), (8192 + 37, "same_step"), (20000, "disabled")])
+def test_delta_observation_equals_full_rewrite_on_the_gpu(fmt, n_envs, mode):
+    """obs_update='delta' against the full rewrite, tensor for tensor after every step: the fused kernel's per-tile
+    decision (70 envs) and k_dyn + k_encode_list of the split step (>= 8,192 envs), with a masked reset and a
+    checkpoint restore in between (see tests/test_emu_parity.py for the CPU twin of this test)."""
+    rows = gen_pool(6, [(1, 1), (2, 3), (4, 4), (6, 6)], RULES_FULL, seed0=33)
+    kw = dict(traceback=True, max_steps=18, autoreset_mode=mode, validate="terminal", obs_format=fmt)
+    a, b = make_env(rows, n_envs, **kw), make_env(rows, n_envs, obs_update="delta", **kw)
+    a.reset(); b.reset()
+    rng = np.random.default_rng(12)
+    ck = None
+    for t in range(50):
+        if t == 20:
+            m = torch.from_numpy(rng.integers(0, 2, n_envs).astype(np.uint8)).cuda()
+            pz = torch.from_numpy(rng.integers(0, len(rows), n_envs).astype(np.int32)).cuda()
+            a.reset(pz, m); b.reset(pz, m)
+        if t == 30:
+            ck = (a.state_dict(), b.state_dict())
+        if t == 40:
+            a.load_state_dict(ck[0]); b.load_state_dict(ck[1])
+            a.encode()
+        act = torch.from_numpy(rng.integers(0, 4, n_envs).astype(np.uint8)).cuda()
+        ra, rb = a.step(act), b.step(act)
+        for k in a.obs:
+            assert torch.equal(a.obs[k], b.obs[k]), (t, k)
+        assert torch.equal(ra[1], rb[1]) and torch.equal(ra[2], rb[2]) and torch.equal(ra[3], rb[3]), t
+        assert torch.equal(ra[4]["rule_flags"], rb[4]["rule_flags"]) and torch.equal(ra[4]["legal_mask"], rb[4]["legal_mask"]), t
+    assert torch.equal(a.stats(), b.stats())

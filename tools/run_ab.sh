@@ -1,18 +1,15 @@
 #!/bin/bash
-# A/B: k_val launched before k_encode (in-tree build) vs after it (build/variants/lib_valafter.so)
-b() { env "$@" python bench.py --steps 500 --warmup 20 --no-e2e --no-cpu-baseline --no-extra $EXTRA 2>/dev/null | python -c "import sys,json; j=json.loads(sys.stdin.read()); r=j['roofline']; print('$* $EXTRA', j['ms_per_step'], r['kernel_ms'], j['gpu_launches'], j['value'], r['frac'], r['whole_step']['frac'])"; }
-python -m pytest tests/test_gpu_parity.py tests/test_gpu_fullsize.py -x -q 2>&1 | tail -2
-OLD=SPARC_B200_LIB=$PWD/build/variants/lib_valafter.so
-for rep in 1 2; do
-EXTRA="--obs-format compact" b A=new
-EXTRA="--obs-format compact" b $OLD
-EXTRA="" b A=new
-EXTRA="" b $OLD
-done
-EXTRA="--obs-format compact" b SPARC_VAL_GRID=64
-EXTRA="--obs-format compact" b SPARC_VAL_GRID=148
-EXTRA="" b SPARC_VAL_GRID=64
-EXTRA="--workload config3" b A=new
-EXTRA="--workload config3" b $OLD
-EXTRA="--no-graph" b A=new
-EXTRA="--no-graph" b $OLD
+# delta observation mode: GPU tests, then step times next to the full rewrite (both formats, with and without validation)
+b() { env "$@" python bench.py --steps 500 --warmup 20 --no-e2e --no-cpu-baseline --no-extra $EXTRA 2>gpurun_out/err.log | python -c "import sys,json; j=json.loads(sys.stdin.read()); r=j['roofline']; print('$* $EXTRA', j['ms_per_step'], r['kernel_ms'], j['gpu_launches'], j['value'], r['algorithmic_bytes_per_env_step'], r['whole_step']['frac'])" || tail -3 gpurun_out/err.log; }
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+EXTRA="" b A=1
+EXTRA="--obs-update delta" b A=1
+EXTRA="--obs-update delta --validate never" b A=1
+EXTRA="--obs-update delta --obs-format compact" b A=1
+EXTRA="--obs-update delta --workload config3" b A=1
+EXTRA="--obs-update delta --workload config2" b A=1
+EXTRA="--workload config2" b A=1
+EXTRA="--obs-update delta" b SPARC_VAL_GRID=64
+EXTRA="--obs-update delta" b SPARC_VAL_GRID=148
+EXTRA="--obs-update delta" b SPARC_VAL_GRID=296
+python bench.py --steps 200 --warmup 10 --obs-update delta --no-extra --cpu-seconds 3 > gpurun_out/bench_config4_delta.json 2>gpurun_out/err2.log; tail -c 600 gpurun_out/bench_config4_delta.json
