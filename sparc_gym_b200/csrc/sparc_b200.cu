@@ -57,7 +57,8 @@ struct SparcEnv {
     uint32_t* vq;
     uint32_t* rq_count;      // update = SPARC_OBS_DELTA: envs that began a new episode this step (count, finished CTAs)
     uint32_t* rq;            // [n_envs]
-    int val_grid;
+    int val_grid;            // CTAs of k_val beside the full-rewrite encoder
+    int val_grid_delta;      // ... when nothing but k_encode_list runs beside it (update = SPARC_OBS_DELTA)
     int ring_grid;           // >0: use k_env_ring with this many persistent CTAs (one per SM)
     unsigned int* sched;     // [2] tile counter + finished-producer counter of k_env_ring
     int64_t launches;
@@ -200,6 +201,12 @@ __global__ void __launch_bounds__(CTA_THREADS) k_val(const KParams p) {
     }
 }
 
+// (k_val_g8 -- eight lanes per snapshot, lane l owning word l of every 16-stride board: a flood sweep is one row_fill,
+// two shuffles and a ballot, the per-region rules run redundantly on the 8 lanes -- was written, verified against
+// k_val on 40 k terminal states, and measured: no faster with one round per group (delta step 0.0514 vs 0.0510 ms at
+// 148 CTAs), twice as slow at 32 CTAs (4 rounds: k_dyn + k_val 78 vs 46 us).  The sweep's dependent chain is as long
+// with one word per lane as with eight words of instruction-level parallelism in one lane, so the instruction count
+// it saves was not the limit.  Removed; profiles/r1_ab_val_g8.txt.)
 #ifndef ENC_THREADS
 #define ENC_THREADS 128
 #endif
@@ -660,6 +667,10 @@ int sparc_env_create(SparcStore* store, int64_t n_envs, int traceback, int max_s
                 e->val_grid = 32;              // x128 threads; a small grid disturbs the co-running encoder least (measured)
                 const char* ve = getenv("SPARC_VAL_GRID");
                 if (ve && atoi(ve) > 0) e->val_grid = atoi(ve);
+                e->val_grid_delta = 148;       // measured, delta step: 32 CTAs 0.0528, 64 0.0512, 148 0.0502, 296 0.0505 ms
+                const char* vd = getenv("SPARC_VAL_GRID_DELTA");
+                if (vd && atoi(vd) > 0) e->val_grid_delta = atoi(vd);
+
             }
             if (se != cudaSuccess) { delete e; return fail(SPARC_E_CUDA, "side stream / queue: %s", cudaGetErrorString(se)); }
             e->split_chunks = nc;
@@ -790,7 +801,8 @@ static int launch_env(SparcEnv* e, KParams& p, void* stream) {
             // from a full register file -- changed nothing: compact 0.0833 vs 0.0833 ms, reference 0.1861 vs 0.1850.)
             if (fork_val) {                                                  // k_val beside (the last) k_encode
                 if (nc == 1) CU(cudaStreamWaitEvent(e->side, e->ev_start, 0));
-                k_val<<<(unsigned)e->val_grid, CTA_THREADS, 0, e->side>>>(p);
+                const unsigned vgrid = (unsigned)(delta ? e->val_grid_delta : e->val_grid);
+                k_val<<<vgrid, CTA_THREADS, 0, e->side>>>(p);
                 CU(cudaEventRecord(e->ev_val, e->side));
                 e->launches++;
                 CU(cudaStreamWaitEvent(s0, e->ev_val, 0));                   // join

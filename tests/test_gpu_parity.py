@@ -275,3 +275,4 @@ def test_delta_observation_equals_full_rewrite_on_the_gpu(fmt, n_envs, mode):
         assert torch.equal(ra[1], rb[1]) and torch.equal(ra[2], rb[2]) and torch.equal(ra[3], rb[3]), t
         assert torch.equal(ra[4]["rule_flags"], rb[4]["rule_flags"]) and torch.equal(ra[4]["legal_mask"], rb[4]["legal_mask"]), t
     assert torch.equal(a.stats(), b.stats())
+
