@@ -242,30 +242,35 @@ __global__ void __launch_bounds__(ENC_THREADS, ENC_MINBLOCKS) k_encode(const KPa
 }
 
 // update = SPARC_OBS_DELTA on the split path: k_dyn touches the changed cells in place and queues the envs that began a
-// new episode (1-2 % per step); this kernel rewrites those in full, one env per CTA pass, and leaves the queue empty.
+// new episode (1-2 % per step); this kernel rewrites those in full and leaves the queue empty.  One WARP per queue
+// entry (rows of tile = 1 in the warp's own slice of shared memory, __syncwarp between the stages): the first
+// version gave every entry a whole CTA and three block barriers and took 16.5 us for ~2,100 envs -- two waves of
+// mostly idle CTAs, each a chain of state load -> store loads -> stores.
 template <int FMT>
 __global__ void __launch_bounds__(ENC_THREADS) k_encode_list(const KParams p) {
     const StoreDev& st = p.st;
-    const int tid = threadIdx.x;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint32_t count = *p.rq_count;
-    uint32_t* head = smem;
-    uint32_t* flats = smem + tile_head_words(1);
-    for (uint32_t slot = blockIdx.x; slot < count; slot += gridDim.x) {
+    const int per_warp = tile_head_words(1) + tile_flat_words(st, 1);
+    uint32_t* head = smem + wib * per_warp;
+    uint32_t* flats = head + tile_head_words(1);
+    const uint32_t nwarps = gridDim.x * (ENC_THREADS / 32);
+    for (uint32_t slot = blockIdx.x * (ENC_THREADS / 32) + wib; slot < count; slot += nwarps) {
         const long long env = (long long)p.rq[slot];
-        if (tid == 0) {
+        if (lane == 0) {
             EnvRegs e;
             load_env(e, p.sd, st, p.cfg.n_envs, env);
             head[SPARC_DYN_STRIDE] = e.puzzle;
             write_dyn(st, head, 0, e);
         }
-        __syncthreads();
-        encode_tile_stage1a(st, head, flats, 1, 1, p.obs, tid, ENC_THREADS);
-        __syncthreads();
-        encode_env_elementwise<FMT>(st, head, flats, env, p.obs, tid, ENC_THREADS);
-        __syncthreads();                                         // the rows are reused by the next pass
+        __syncwarp();
+        encode_tile_stage1a(st, head, flats, 1, 1, p.obs, lane, 32);
+        __syncwarp();
+        encode_env_elementwise<FMT>(st, head, flats, env, p.obs, lane, 32);
+        __syncwarp();                                            // the rows are reused by the next pass
     }
     __syncthreads();                                             // every thread of the CTA has read `count`
-    if (tid == 0) {                                              // last CTA out empties the queue for the next step
+    if (threadIdx.x == 0) {                                      // last CTA out empties the queue for the next step
         __threadfence();
         if (atomicAdd(p.rq_count + 1, 1u) == gridDim.x - 1) { p.rq_count[0] = 0; p.rq_count[1] = 0; }
     }
@@ -776,11 +781,12 @@ static int launch_env(SparcEnv* e, KParams& p, void* stream) {
             if (nc == 1 && (fork_val || fork_copy)) CU(cudaEventRecord(e->ev_start, s0));   // = k_dyn done
             if (delta) {
                 if (last) {                                                  // the envs that began a new episode, in full
-                    const size_t shmem1 = (size_t)(tile_head_words(1) + tile_flat_words(p.st, 1)) * sizeof(uint32_t);
-                    // ~1.6 % of the envs end an episode per step under random play: one queue entry per CTA pass when the
-                    // grid covers n / 32 entries (CTAs beyond the queue length leave at once)
-                    const int64_t want = (n + 31) / 32;
-                    const unsigned lgrid = (unsigned)(want < 148 ? (n < 148 ? n : 148) : (want > 148 * 32 ? 148 * 32 : want));
+                    const size_t shmem1 = (size_t)(ENC_THREADS / 32) * (tile_head_words(1) + tile_flat_words(p.st, 1)) * sizeof(uint32_t);
+                    // ~1.6 % of the envs end an episode per step under random play: one queue entry per warp pass when the
+                    // grid's warps cover n / 32 entries; at most one resident wave (warps beyond the queue leave at once)
+                    int64_t want = (n + 127) / 128;
+                    if (want > 148 * 8) want = 148 * 8;
+                    const unsigned lgrid = (unsigned)(want < 1 ? 1 : want);
                     if (compact) k_encode_list<SPARC_OBS_COMPACT><<<lgrid, ENC_THREADS, shmem1, s0>>>(p);
                     else k_encode_list<SPARC_OBS_REFERENCE><<<lgrid, ENC_THREADS, shmem1, s0>>>(p);
                 }
