@@ -38,6 +38,14 @@ for rows in pools:
         rng = np.random.default_rng(tile)
         for t in range(40):
             env.step(rng.integers(0, 4, N).astype(np.uint8))
+    # delta observation update: in-place plane writes + the per-env rewrite of k_encode_list (rows of tile = 1)
+    for fmt, defer, tile in (("reference", True, 8), ("compact", True, 32), ("reference", False, 4)):
+        env = EmuVecEnv(rows, 45, traceback=True, max_steps=11, autoreset_mode="same_step", validate="terminal",
+                        tile=tile, obs_format=fmt, obs_update="delta", defer_validation=defer)
+        env.reset()
+        rng = np.random.default_rng(9)
+        for t in range(40):
+            env.step(rng.integers(0, 4, 45).astype(np.uint8))
 print("sanitizer run ok")
 """ % (ROOT, HERE, os.path.join(ROOT, "oracle"))
 
