@@ -9,6 +9,7 @@ Outputs (committed; the GPU box has no /root/reference):
   resets.json.gz    puzzle-cursor behaviour of reset(seed=...) / reset() / reset(options=...)
   ingest.json.gz    `_process_puzzles` results on rows that exercise the ingest quirks
   sparc_text.json.gz  observation='SPaRC' strings, step by step
+  config1.json.gz   BASELINE configs[0]: the 10,000-step random rollout of one 4x4 gaps+dots puzzle, step by step
 """
 from __future__ import annotations
 
@@ -63,6 +64,52 @@ def make_traces():
                 episodes.append({"row": i, "traceback": tb, "max_steps": 40,
                                  "actions": acts[:max(len(trace) - 1, 0)], "trace": trace})
     dump("traces.json.gz", {"rows": rows, "episodes": episodes})
+
+
+def obs_crc(obs):
+    """CRC32 over the observation exactly as the reference holds it: base planes in the puzzle's key order
+    (int32[X, Y] each), then color (int32), then additional_info (int64)."""
+    import zlib
+    c = 0
+    for k in obs["base"]:
+        c = zlib.crc32(np.ascontiguousarray(obs["base"][k], np.int32).tobytes(), c)
+    c = zlib.crc32(np.ascontiguousarray(obs["color"], np.int32).tobytes(), c)
+    return zlib.crc32(np.ascontiguousarray(obs["additional_info"], np.int64).tobytes(), c)
+
+
+CONFIG1 = dict(w=4, h=4, seed=0, T=10000, max_steps=1000, action_seed=0)
+
+
+def config1_actions():
+    return np.random.default_rng(CONFIG1["action_seed"]).integers(0, 4, size=CONFIG1["T"], dtype=np.uint8)
+
+
+def make_config1():
+    """BASELINE configs[0]: one 4x4 gaps+dots puzzle, observation='new', traceback=False, max_steps=1000,
+    10,000 random actions, reset onto the same puzzle when an episode ends (the reference's plane leak undone
+    first).  Per step: reward (type + value), terminated, truncated, legal actions, agent location,
+    current_step, all_rules_satisfied and a CRC32 of the whole observation."""
+    row = gen_puzzle(CONFIG1["w"], CONFIG1["h"], CONFIG1["seed"], RULES_GAPS_DOTS)
+    ref = rh.make_reference_env([row], observation="new", traceback=False, max_steps=CONFIG1["max_steps"])
+    rh.zero_leak(ref)
+    obs, info = ref.reset(options={"puzzle_id": row["id"]})
+    out = {"reset_crc": obs_crc(obs), "keys": list(obs["base"].keys()), "reward": [], "term": [], "trunc": [],
+           "legal": [], "agent": [], "step": [], "rules": [], "crc": [], "episodes": 0}
+    for a in config1_actions().tolist():
+        obs, r, te, tr, info = ref.step(a)
+        out["reward"].append([type(r).__name__, float(r)])
+        out["term"].append(int(bool(te))); out["trunc"].append(int(bool(tr)))
+        out["legal"].append(sum(1 << int(x) for x in info["legal_actions"]))
+        out["agent"].append([int(v) for v in info["agent_location"]])
+        out["step"].append(int(info["current_step"]))
+        out["rules"].append(int(bool(info["rule_status"]["all_rules_satisfied"]["passed"])))
+        out["crc"].append(obs_crc(obs))
+        if te or tr:
+            out["episodes"] += 1
+            rh.zero_leak(ref)
+            obs, info = ref.reset(options={"puzzle_id": row["id"]})
+            assert obs_crc(obs) == out["reset_crc"]
+    dump("config1.json.gz", {"config": CONFIG1, "row": row, "golden": out})
 
 
 def make_polyfit():
@@ -231,3 +278,4 @@ if __name__ == "__main__":
     make_resets()
     make_polyfit()
     make_traces()
+    make_config1()

@@ -133,3 +133,40 @@ def compare(env_out, exp, what, check_flags=None, check_obs=True, only=None):
                     f"{what}: env {i} rule flags {got[i] & 0x1FF:09b} != oracle {exp['flags'][i]:09b}"
             else:
                 assert got[i] == 0, f"{what}: env {i} has stale rule flags"
+
+
+# ---- BASELINE configs[0]: the reference's own CPU-runnable case, recorded step by step (tests/golden/config1.json.gz) ----
+def obs_crc(obs):
+    """CRC32 over the observation as the reference holds it: base planes in the puzzle's key order (int32[X, Y]
+    each), then color (int32), then additional_info (int64).  (Same function as tests/golden/make_golden.py.)"""
+    import zlib
+    c = 0
+    for k in obs["base"]:
+        c = zlib.crc32(np.ascontiguousarray(to_np(obs["base"][k]), np.int32).tobytes(), c)
+    c = zlib.crc32(np.ascontiguousarray(to_np(obs["color"]), np.int32).tobytes(), c)
+    return zlib.crc32(np.ascontiguousarray(to_np(obs["additional_info"]), np.int64).tobytes(), c)
+
+
+def replay_config1(env, g, n_steps=None):
+    """Drive a single env with the reference's call surface (reset(options=...) / step(a)) through the recorded
+    config-1 rollout and compare every step with what the unmodified reference returned: reward value AND type,
+    terminated, truncated, legal actions, agent location, current_step, all_rules_satisfied and the CRC of the
+    whole observation; resets onto the same puzzle whenever an episode ends, like the recording."""
+    cfg, row, gold = g["config"], g["row"], g["golden"]
+    acts = np.random.default_rng(cfg["action_seed"]).integers(0, 4, size=cfg["T"], dtype=np.uint8).tolist()
+    obs, info = env.reset(options={"puzzle_id": row["id"]})
+    assert list(obs["base"].keys()) == gold["keys"] and obs_crc(obs) == gold["reset_crc"]
+    episodes = 0
+    for t, a in enumerate(acts[:n_steps]):
+        obs, r, te, tr, info = env.step(a)
+        got = ([type(r).__name__, float(r)], int(bool(te)), int(bool(tr)), sum(1 << int(x) for x in info["legal_actions"]),
+               [int(v) for v in info["agent_location"]], int(info["current_step"]),
+               int(bool(info["rule_status"]["all_rules_satisfied"]["passed"])), obs_crc(obs))
+        want = (gold["reward"][t], gold["term"][t], gold["trunc"][t], gold["legal"][t], gold["agent"][t], gold["step"][t],
+                gold["rules"][t], gold["crc"][t])
+        assert got == want, (t, got, want)
+        if te or tr:
+            episodes += 1
+            obs, info = env.reset(options={"puzzle_id": row["id"]})
+            assert obs_crc(obs) == gold["reset_crc"], t
+    return episodes

@@ -94,3 +94,14 @@ def test_dropin_host_logic_text_mode_and_cursor(dropin):
         else:
             env.reset(seed=s[1], options={"puzzle_id": s[2]})
         assert env.current_puzzle_index == want, s
+
+
+def test_dropin_host_logic_config1_rollout(dropin):
+    """BASELINE configs[0] through the drop-in (gym.make surface) over the host build of the device code: the first
+    3,000 of the 10,000 recorded steps, every output incl. the CRC of the whole observation
+    (tests/test_gpu_gym_dropin.py replays all of them on the GPU)."""
+    from parity import replay_config1
+    with gzip.open(os.path.join(G, "config1.json.gz"), "rb") as f:
+        g = json.loads(f.read())
+    env = dropin.make("SPaRc-Gym", puzzles=[g["row"]], observation="new", traceback=False, max_steps=g["config"]["max_steps"])
+    assert replay_config1(env, g, n_steps=3000) > 30

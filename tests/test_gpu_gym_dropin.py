@@ -65,3 +65,17 @@ def test_dropin_sparc_text_observation_matches_reference():
         for a, want in zip(ep["actions"], ep["trace"][1:]):
             obs, r, te, tr, info = env.step(a)
             assert [obs, [type(r).__name__, float(r)], te, tr, info["legal_actions"]] == want
+
+
+def test_dropin_config1_rollout_matches_reference():
+    """BASELINE configs[0] on the GPU: gym.make(..., observation='new', traceback=False, max_steps=1000) on one 4x4
+    gaps+dots puzzle, the recorded 10,000 random steps of the unmodified reference, every output of every step
+    (reward value and type, flags, legal actions, agent, step counter, all_rules_satisfied, CRC of the observation)."""
+    import gzip, json, os
+    import sparc_gym_b200
+    from parity import replay_config1
+    with gzip.open(os.path.join(os.path.dirname(__file__), "golden", "config1.json.gz"), "rb") as f:
+        g = json.loads(f.read())
+    env = sparc_gym_b200.make("SPaRc-Gym", puzzles=[g["row"]], observation="new", traceback=False,
+                              max_steps=g["config"]["max_steps"])
+    assert replay_config1(env, g) == g["golden"]["episodes"] > 100

@@ -111,3 +111,12 @@ def test_sparc_text_observation_matches_reference():
         for a, want in zip(ep["actions"], ep["trace"][1:]):
             obs, r, te, tr, info = env.step(a)
             assert [obs, [type(r).__name__, float(r)], te, tr, info["legal_actions"]] == want
+
+
+def test_config1_rollout_matches_reference():
+    """BASELINE configs[0]: 10,000 random steps on one 4x4 gaps+dots puzzle (observation='new', traceback=False,
+    max_steps=1000), every step against the recording of the unmodified reference."""
+    from parity import replay_config1
+    g = load("config1.json.gz")
+    env = so.OracleEnv([g["row"]], observation="new", traceback=False, max_steps=g["config"]["max_steps"])
+    assert replay_config1(env, g) == g["golden"]["episodes"] > 100
