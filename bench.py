@@ -231,7 +231,7 @@ def main():
     env = runner.env
     st = env.store
     t_build = time.perf_counter() - t_build
-    K, W = args.steps, args.warmup
+    K, W = max(1, args.steps), max(3, args.warmup)        # timing rule: at least 3 untimed warm-up steps
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     actions = torch.randint(0, 4, (K + W, n_env), dtype=torch.uint8, device=dev, generator=gen)
     sampler = ClockSampler(local_rank) if rank == 0 else None     # samples through warm-up, timed steps and e2e
