@@ -948,6 +948,19 @@ int sparc_debug_counters(SparcEnv* e, uint64_t* out5_host) {   /* RING_PROFILE b
     return SPARC_OK;
 }
 
+int sparc_debug_valprof(uint64_t* out8_host, int clear) {     /* -DVAL_PROFILE builds only: see VP_* in sparc_core.cuh, tools/valprof.py */
+#ifdef VAL_PROFILE
+    if (!out8_host) return fail(SPARC_E_ARG, "null argument%s");
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpyFromSymbol(out8_host, g_valprof, 8 * sizeof(uint64_t)));
+    if (clear) { const unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0}; CU(cudaMemcpyToSymbol(g_valprof, z, sizeof(z))); }
+    return SPARC_OK;
+#else
+    (void)out8_host; (void)clear;
+    return fail(SPARC_E_ARG, "not a -DVAL_PROFILE build%s");
+#endif
+}
+
 int64_t sparc_env_num_envs(const SparcEnv* e) { return e ? e->cfg.n_envs : 0; }
 int sparc_kernel_launches(const SparcEnv* e, int64_t* out_count) {
     if (!e || !out_count) return fail(SPARC_E_ARG, "null argument%s");

@@ -19,6 +19,30 @@ static long long g_fit_iters = 0, g_fit_calls = 0, g_fit_max = 0, g_fit_cur = 0;
 #define SPARC_COUNT_FIT_CALL() ((void)0)
 #endif
 
+// -DVAL_PROFILE (tools/valprof.py): cycle counters of validate_env per queued terminal state -- where the ~30 us of
+// k_val's slowest snapshot go.  g_valprof = sum total, sum prologue, sum flood fill, sum exact fit, snapshots,
+// max total, max flood fill, max exact fit.  Not compiled otherwise.
+#if defined(VAL_PROFILE) && defined(__CUDACC__)
+__device__ unsigned long long g_valprof[8];
+#endif
+#if defined(VAL_PROFILE) && defined(__CUDA_ARCH__)
+#define VP_BEGIN() long long vp_t0 = clock64(), vp_pro = 0, vp_flood = 0, vp_fit = 0, vp_tmp = 0
+#define VP_PROLOGUE_DONE() (vp_pro = clock64() - vp_t0)
+#define VP_TIC() (vp_tmp = clock64())
+#define VP_TOC(acc) ((acc) += clock64() - vp_tmp)
+#define VP_END() do { const unsigned long long vp_tot = (unsigned long long)(clock64() - vp_t0); \
+    atomicAdd(&g_valprof[0], vp_tot); atomicAdd(&g_valprof[1], (unsigned long long)vp_pro); \
+    atomicAdd(&g_valprof[2], (unsigned long long)vp_flood); atomicAdd(&g_valprof[3], (unsigned long long)vp_fit); \
+    atomicAdd(&g_valprof[4], 1ull); atomicMax(&g_valprof[5], vp_tot); atomicMax(&g_valprof[6], (unsigned long long)vp_flood); \
+    atomicMax(&g_valprof[7], (unsigned long long)vp_fit); } while (0)
+#else
+#define VP_BEGIN() ((void)0)
+#define VP_PROLOGUE_DONE() ((void)0)
+#define VP_TIC() ((void)0)
+#define VP_TOC(acc) ((void)0)
+#define VP_END() ((void)0)
+#endif
+
 #if defined(__CUDACC__)
 #define SPARC_HD __host__ __device__ __forceinline__
 #define SPARC_D __device__ __forceinline__
@@ -538,6 +562,7 @@ SPARC_HD bool exact_fit(uint64_t region, int w, int h, const SparcShape* shapes,
 // first failure.
 SPARC_HD int validate_env(const StoreDev& st, uint32_t puzzle, const uint32_t* vd, int ax, int ay,
                           int8_t* region_map, int8_t* region_fit = nullptr) {
+    VP_BEGIN();
     const HdrRegs h = load_hdr(st, puzzle);
     const uint32_t* nbp = st.nb + (size_t)puzzle * SPARC_N_NODE_BOARDS * 8;
     // visited: dense -> 16-stride
@@ -592,6 +617,8 @@ SPARC_HD int validate_env(const StoreDev& st, uint32_t puzzle, const uint32_t* v
     if (!(h.flags & 2) && !region_map && !region_fit) {
         flags |= SPARC_RULE_SQUARES | SPARC_RULE_STARS | SPARC_RULE_POLY_YLOP;
         if ((flags & 0xFF) == 0xFF) flags |= SPARC_RULE_ALL;
+        VP_PROLOGUE_DONE();
+        VP_END();
         return flags;
     }
     uint32_t Pm[8], unl[8];
@@ -607,6 +634,7 @@ SPARC_HD int validate_env(const StoreDev& st, uint32_t puzzle, const uint32_t* v
     const int w = (h.X - 1) >> 1, hh = (h.Y - 1) >> 1;
     bool sq_ok = true, star_ok = true, poly_ok = true;
     int rid = 0;
+    VP_PROLOGUE_DONE();
     for (;;) {
         int k0 = -1;
 #pragma unroll
@@ -616,6 +644,7 @@ SPARC_HD int validate_env(const StoreDev& st, uint32_t puzzle, const uint32_t* v
         const uint32_t seed = board_word(unl, k0) & (0u - board_word(unl, k0));    // lowest set bit: raster order
 #pragma unroll
         for (int k = 0; k < 8; k++) f[k] = (k == k0) ? seed : 0u;
+        VP_TIC();
         for (;;) {                                                              // flood to fix-point
             uint32_t g[8], ch = 0;
 #pragma unroll
@@ -630,6 +659,7 @@ SPARC_HD int validate_env(const StoreDev& st, uint32_t puzzle, const uint32_t* v
             }
             if (!ch) break;
         }
+        VP_TOC(vp_flood);
         uint64_t R = 0;                                     // component -> rule-cell board
 #pragma unroll
         for (int cx = 0; cx < 7; cx++) {
@@ -677,8 +707,10 @@ SPARC_HD int validate_env(const StoreDev& st, uint32_t puzzle, const uint32_t* v
             }
             if (any) {
                 int verdict = SPARC_FIT_OK;
+                VP_TIC();
                 if (net != sp_popcll(R)) verdict = SPARC_FIT_AREA_MISMATCH;   // SG.py:679-682
                 else if (!exact_fit(R, w, hh, shapes, h.n_shapes, np, nyl)) verdict = SPARC_FIT_NO_TILING;
+                VP_TOC(vp_fit);
                 if (verdict != SPARC_FIT_OK) poly_ok = false;
                 if (region_fit && rid < SPARC_MAX_REGIONS) region_fit[rid] = (int8_t)verdict;
             }
@@ -689,6 +721,7 @@ SPARC_HD int validate_env(const StoreDev& st, uint32_t puzzle, const uint32_t* v
     if (star_ok) flags |= SPARC_RULE_STARS;
     if (poly_ok) flags |= SPARC_RULE_POLY_YLOP;
     if ((flags & 0xFF) == 0xFF) flags |= SPARC_RULE_ALL;                        // SG.py:932-935
+    VP_END();
     return flags;
 }
 
