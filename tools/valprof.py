@@ -20,8 +20,9 @@ ap.add_argument("--obs-update", default="delta")
 ap.add_argument("--obs-format", default="reference")
 ap.add_argument("--envs", type=int, default=131072)
 ap.add_argument("--steps", type=int, default=100)
+ap.add_argument("--pool", type=int, default=4096)
 a = ap.parse_args()
-rows = config_pool(4, n_puzzles=4096)
+rows = config_pool(4, n_puzzles=a.pool)
 env = SparcVecEnv(rows, a.envs, traceback=False, max_steps=1000, autoreset_mode="same_step", validate="terminal",
                   obs_format=a.obs_format, obs_update=a.obs_update)
 env.reset()
