@@ -20,7 +20,9 @@ G = os.path.join(os.path.dirname(__file__), "golden")
 class EmuTorchVecEnv(EmuVecEnv):
     """EmuVecEnv with SparcVecEnv's tensor-typed surface (torch views of the same numpy buffers)."""
 
-    def __init__(self, puzzles, num_envs, device=None, **kw):
+    device = torch.device("cpu")
+
+    def __init__(self, puzzles, num_envs, device=None, write_obs=True, **kw):
         super().__init__(puzzles, num_envs, **kw)
         self._np = {k: getattr(self, k) for k in ("reward", "reward_code", "terminated", "truncated", "legal_mask",
                                                    "step_count", "agent_xy")}
@@ -36,8 +38,9 @@ class EmuTorchVecEnv(EmuVecEnv):
 
     def validate(self, **kw):
         out = super().validate(**kw)
-        return tuple(torch.from_numpy(np.ascontiguousarray(o).view(np.int16) if o.dtype == np.uint16 else o)
-                     for o in (out if isinstance(out, tuple) else (out,)))
+        res = tuple(torch.from_numpy(np.ascontiguousarray(o).view(np.int16) if o.dtype == np.uint16 else o)
+                    for o in (out if isinstance(out, tuple) else (out,)))
+        return res if len(res) > 1 else res[0]          # like SparcVecEnv.validate: the flags alone when nothing else is asked for
 
     def close(self):
         pass
@@ -105,3 +108,36 @@ def test_dropin_host_logic_config1_rollout(dropin):
         g = json.loads(f.read())
     env = dropin.make("SPaRc-Gym", puzzles=[g["row"]], observation="new", traceback=False, max_steps=g["config"]["max_steps"])
     assert replay_config1(env, g, n_steps=3000) > 30
+
+
+def test_verify_paths_host_logic(monkeypatch):
+    """sparc_gym_b200.verify.verify_paths (the LLM-evaluation caller's env work as one batched call) over the host
+    build: listed solutions are solved and satisfy every rule, their prefixes are neither; return, step count and
+    flags against the oracle replaying the same actions one env at a time (GPU twin: tests/test_gpu_verify.py)."""
+    import sparc_oracle as so
+    import sparc_gym_b200.verify as vf
+    from sparc_gym_b200.dataset import RULES_FULL, gen_pool
+    monkeypatch.setattr(vf, "SparcVecEnv", EmuTorchVecEnv)
+    rows = gen_pool(10, [(3, 3), (4, 4), (5, 5)], RULES_FULL, seed0=700, extra_solutions=1)
+    idx, paths = [], []
+    for i, r in enumerate(rows):
+        sol = [(p["x"], p["y"]) for p in r["solutions"][0]["path"]]
+        idx += [i, i, i]
+        paths += [sol, sol[:max(2, len(sol) // 2)], sol[:3] + [sol[1]] + sol[3:]]
+    res = vf.verify_paths(rows, idx, paths, device="cpu")
+    assert res["solved"][0::3].all() and res["all_rules_satisfied"][0::3].all() and res["terminated"][0::3].all()
+    assert not res["solved"][1::3].any() and not res["reached_target"][1::3].any()
+    env = so.OracleEnv(rows, max_steps=10 ** 6)
+    for k, (i, p) in enumerate(zip(idx, paths)):
+        env.reset(options={"puzzle_id": rows[i]["id"]})
+        total, n, te, tr, info = 0, 0, False, False, env._info()
+        for a in vf.path_to_actions(p):
+            _, r, te, tr, info = env.step(a)
+            total += round(r * 100)
+            n += 1
+            if te or tr:
+                break
+        assert res["return_cents"][k] == total and res["steps"][k] == n, k
+        assert bool(res["terminated"][k]) == te and bool(res["truncated"][k]) == tr, k
+        for name in so.RULE_NAMES:
+            assert bool(res[name][k]) == info["rule_status"][name]["passed"], (k, name)
