@@ -34,6 +34,8 @@ WORKLOADS = {
     "config2": (2, 4096, 64, False, 1000, "4,096 lockstep envs, 4x4 gaps+dots puzzles (9x9 lattice, 5 planes)"),
     "config3": (3, 65536, 1024, True, 1000, "65,536 envs, mixed 3x3-6x6 full-rule puzzles padded to 13x13, traceback, terminal validation"),
     "config4": (4, 131072, 4096, False, 1000, "131,072 envs per GPU (1M on 8 GPUs), 6x6 full rule set, 8 colours (13x13 lattice, 10 planes)"),
+    # BASELINE configs[4]: the env-count sweep; one point per run (--envs-per-gpu N), tools/env_sweep.py drives 2^10..2^22
+    "config5": (5, 65536, 1024, True, 1000, "env-count sweep point: --envs-per-gpu N envs per GPU, heterogeneous 3x3-6x6 full-rule puzzles padded to 13x13, traceback"),
 }
 
 
@@ -116,49 +118,139 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU arm: the reference's algorithm (oracle port, reference_cost=True) on the host cores
+# CPU arm: the UNMODIFIED reference env (baseline/_ref or /root/reference, through oracle/refharness.py) on the host
+# cores, one env per worker process -- AsyncVectorEnv's architecture.  Falls back to the oracle port
+# (oracle/sparc_oracle.py, reference_cost=True) only when no reference tree is installed, and says so in `kind`.
 # ------------------------------------------------------------------------------------------------
-def _cpu_worker(args):
-    rows, traceback, max_steps, budget_s, seed = args
+_W = {}            # per-worker state (the env lives across samples: the reference's ctor re-parses every row)
+
+
+def _cpu_worker_init(rows_by_worker, traceback, max_steps, kind, counter):
+    with counter.get_lock():
+        w = counter.value
+        counter.value += 1
+    rows = rows_by_worker[w]
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import sparc_oracle as so
-    env = so.OracleEnv(rows, observation="new", traceback=traceback, max_steps=max_steps, reference_cost=True)
-    rng = np.random.default_rng(seed)
-    k = 0
-    env.reset(options={"puzzle_id": rows[0]["id"]})
-    acts = rng.integers(0, 4, 1 << 16)
-    n = 0
+    if kind == "reference":
+        import refharness as rh
+        env = rh.make_reference_env(rows, observation="new", traceback=traceback, max_steps=max_steps)
+        _W["zero_leak"] = rh.zero_leak
+    else:
+        import sparc_oracle as so
+        env = so.OracleEnv(rows, observation="new", traceback=traceback, max_steps=max_steps, reference_cost=True)
+        _W["zero_leak"] = None
+    _W.update(env=env, rows=rows, k=0, acts=np.random.default_rng(w).integers(0, 4, 1 << 16), n=0, fresh=True)
+
+
+def _cpu_reset():
+    env, k = _W["env"], _W["k"]
+    if _W["zero_leak"]:
+        _W["zero_leak"](env, k)                     # the reference leaks visited / agent planes across episodes
+    env.reset(options={"puzzle_id": _W["rows"][k]["id"]})
+
+
+def _cpu_sample(budget_s):
+    """`budget_s` seconds of random-action steps on this worker's env, resetting (next puzzle) when an episode ends."""
+    env, acts = _W["env"], _W["acts"]
+    if _W["fresh"]:
+        _cpu_reset()
+        _W["fresh"] = False
+    n0, n = _W["n"], _W["n"]
     t0 = time.perf_counter()
     while time.perf_counter() - t0 < budget_s:
         _, _, te, tr, _ = env.step(int(acts[n & 0xFFFF]))
         n += 1
         if te or tr:
-            k = (k + 1) % len(rows)
-            env.reset(options={"puzzle_id": rows[k]["id"]})
-    return n, time.perf_counter() - t0
+            _W["k"] = (_W["k"] + 1) % len(_W["rows"])
+            _cpu_reset()
+    _W["n"] = n
+    return n - n0, time.perf_counter() - t0
 
 
-def cpu_baseline(workload, budget_s=12.0, cores=None):
-    """Oracle port of the reference env (two validations per step etc., like SG.py:1111-1238), one
-    env per worker process on every host core -- AsyncVectorEnv's architecture (gymnasium itself
-    is not installed on these boxes)."""
-    import multiprocessing as mp
-    from sparc_gym_b200.dataset import config_pool
-    cfg, _, _, traceback, max_steps, _ = WORKLOADS[workload]
-    cores = cores or os.cpu_count() or 1
-    rows = config_pool(cfg, n_puzzles=8 * cores)       # bounded sample of the pool: 8 puzzles per worker
-    jobs = [(rows[8 * w:8 * w + 8], traceback, max_steps, budget_s, w) for w in range(cores)]
-    t0 = time.perf_counter()
-    with mp.get_context("fork").Pool(cores) as pool:
-        res = pool.map(_cpu_worker, jobs)
-    wall = time.perf_counter() - t0
-    steps = sum(r[0] for r in res)
-    rate = sum(r[0] / r[1] for r in res)
-    return {"value": round(rate, 1), "unit": "env-steps/s", "cores": cores, "kind": "port",
-            "sample": f"{steps} random-action steps of the {workload} puzzles ({8 * cores} of the pool), one oracle env "
-                      f"(oracle/sparc_oracle.py, reference_cost=True) per worker process, {budget_s:.0f}s per worker, "
-                      f"rate = sum of per-worker step rates; wall incl. start-up {wall:.1f}s; "
-                      "AsyncVectorEnv stand-in (gymnasium absent)"}
+class CpuArm:
+    """Worker pool of CPU envs over a bounded sample of the workload's puzzles (8 per worker)."""
+
+    def __init__(self, workload, kind=None, cores=None):
+        import multiprocessing as mp
+        from sparc_gym_b200.dataset import config_pool
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import refharness as rh
+        cfg, _, _, traceback, max_steps, _ = WORKLOADS[workload]
+        self.workload = workload
+        self.cores = cores or os.cpu_count() or 1
+        self.kind = kind or ("reference" if rh.reference_available() else "port")
+        self.ref_root = rh.REFERENCE_ROOT if self.kind == "reference" else None
+        rows = config_pool(cfg, n_puzzles=8 * self.cores)
+        by_worker = [rows[8 * w:8 * w + 8] for w in range(self.cores)]
+        ctx = mp.get_context("fork")
+        self.pool = ctx.Pool(self.cores, initializer=_cpu_worker_init,
+                             initargs=(by_worker, traceback, max_steps, self.kind, ctx.Value("i", 0)))
+
+    def sample(self, budget_s):
+        """One bounded sample: every worker steps for `budget_s` seconds.  Returns (steps, env-steps/s summed over workers)."""
+        res = self.pool.map(_cpu_sample, [budget_s] * self.cores, chunksize=1)
+        return sum(r[0] for r in res), sum(r[0] / r[1] for r in res)
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+    def describe(self, steps, budget_s, n_samples):
+        what = ("the UNMODIFIED reference env (SPaRC_Gym.SPaRC_Gym from %s, stub gymnasium/pygame modules, rows injected "
+                "through datasets.load_dataset, Q1 plane leak zeroed before each reset)" % os.path.relpath(self.ref_root, ROOT)
+                if self.kind == "reference" else "the oracle port (oracle/sparc_oracle.py, reference_cost=True)")
+        return (f"{steps} random-action steps of the {self.workload} puzzles ({8 * self.cores} of the pool, 8 per worker) on {what}, "
+                f"one env per worker process, {n_samples} sample(s) of {budget_s:.1f}s per worker, rate = sum of per-worker "
+                "step rates averaged over the samples; AsyncVectorEnv stand-in (gymnasium absent)")
+
+
+def cpu_baseline(workload, budget_s=10.0, samples=1, warmup=0, kind=None, cores=None, with_port=False):
+    arm = CpuArm(workload, kind=kind, cores=cores)
+    for _ in range(warmup):
+        arm.sample(budget_s)
+    tot, rates = 0, []
+    for _ in range(samples):
+        n, r = arm.sample(budget_s)
+        tot += n
+        rates.append(r)
+    arm.close()
+    out = {"value": round(sum(rates) / len(rates), 1), "unit": "env-steps/s", "cores": arm.cores, "kind": arm.kind,
+           "sample": arm.describe(tot, budget_s, samples), "per_sample": [round(r, 1) for r in rates]}
+    if with_port and arm.kind == "reference":
+        port = CpuArm(workload, kind="port", cores=cores)
+        _, r = port.sample(min(budget_s, 5.0))
+        port.close()
+        out["port_value"] = round(r, 1)
+        out["port_note"] = ("the oracle port (reference_cost=True) on the same puzzles and cores, one sample: "
+                            "%.2fx the unmodified reference" % (r / max(out["value"], 1e-9)))
+    return out
+
+
+def workload_config(args, world, store=None):
+    """The `config` object of the JSON line: the workload only, identical in both arms (run details go to `run`)."""
+    cfg, n_env, pool_n, traceback, max_steps, desc = WORKLOADS[args.workload]
+    n_env = args.envs_per_gpu or n_env
+    pool_n = args.pool or pool_n
+    if store is None:
+        from sparc_gym_b200.dataset import config_pool
+        from sparc_gym_b200.ingest import ingest_rows
+        from sparc_gym_b200.store import PuzzleStore
+        store = PuzzleStore(ingest_rows(config_pool(cfg, n_puzzles=pool_n)))
+    return {"workload": args.workload, "description": desc, "envs_per_gpu": n_env, "global_envs": n_env * world,
+            "pool_puzzles": pool_n, "lattice": [store.slab_x, store.slab_y], "planes": list(store.plane_keys),
+            "traceback": traceback, "max_steps": max_steps, "autoreset": args.autoreset, "validate": args.validate,
+            "obs_format": args.obs_format, "obs_update": args.obs_update,
+            "l2": _l2_note(store.algorithmic_bytes_per_step(args.obs_format) * n_env, args.obs_update),
+            "parallelism": f"env-sharded x{world}, no data-path collective"}
+
+
+def _l2_note(step_bytes, update):
+    if update == "delta":
+        return "delta update: a step touches a few cells per env (L2-resident); latency-bound, not an HBM measurement"
+    if step_bytes > 126e6:
+        return "no flush needed: every step rewrites %.0f MB of observation, more than the 126 MB L2" % (step_bytes / 1e6)
+    return ("observation per step (%.1f MB) fits in the 126 MB L2: writes may be absorbed by L2, the number is "
+            "launch/latency-bound and not an HBM measurement" % (step_bytes / 1e6))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -195,19 +287,19 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        steps_rates = []
-        for _ in range(max(1, min(args.steps, 3))):        # each "step" = one bounded CPU sample
-            steps_rates.append(cpu_baseline(args.workload, budget_s=min(args.cpu_seconds, 10.0)))
-        best = max(steps_rates, key=lambda d: d["value"])
-        print(json.dumps({"impl": "reference", "metric": "env-steps/sec (whole box)", "value": best["value"],
-                          "unit": "env-steps/s", "n_gpus": args.gpus, "steps": len(steps_rates), "warmup": 0,
-                          "ms_per_step": round(1e3 * min(args.cpu_seconds, 10.0), 1),      # one step = one bounded CPU sample
+        # One "step" of this arm = one bounded sample: every host core runs the reference's step() on its own env for
+        # `budget` seconds.  K timed samples after W warm-up samples, sized so that the whole run ends within ~2.5 min.
+        K, W = max(1, args.steps), max(0, args.warmup)
+        budget = max(0.5, min(args.cpu_seconds, 150.0 / (K + W)))
+        cb = cpu_baseline(args.workload, budget_s=budget, samples=K, warmup=W, with_port=not args.no_extra)
+        print(json.dumps({"impl": "reference", "metric": "env-steps/sec (whole box)", "value": cb["value"],
+                          "unit": "env-steps/s", "n_gpus": args.gpus, "steps": K, "warmup": W,
+                          "ms_per_step": round(1e3 * budget, 1),                    # one step = one bounded CPU sample
                           "host_only": True, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                           "dtype": "int32", "data": "synthetic",
-                          "config": {"workload": args.workload, "description": desc, "traceback": traceback,
-                                     "max_steps": max_steps},
-                          "cpu_baseline": best,
-                          "e2e": {"value": best["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0,
+                          "config": workload_config(args, world),
+                          "cpu_baseline": cb,
+                          "e2e": {"value": cb["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0,
                                   "d2h_bytes_per_step": 0}}))
         return
 
@@ -358,22 +450,16 @@ def main():
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": round(ms_max / K, 5),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
             "data": "synthetic",
-            "config": {"workload": args.workload, "description": desc, "envs_per_gpu": n_env,
-                       "global_envs": n_env * world, "pool_puzzles": pool_n, "lattice": [st.slab_x, st.slab_y],
-                       "planes": st.plane_keys, "traceback": traceback, "max_steps": max_steps,
-                       "autoreset": args.autoreset, "validate": args.validate,
-                       "launch": ("one CUDA graph of the K steps" if graph is not None else "K steps launched from Python")
-                                 + f" ({launches // K} kernel launches per step)",
-                       "obs_mode": ("full rewrite" if args.obs_update == "rewrite" else
-                                    "DELTA: persistent observation touched in place, envs that begin a new episode rewritten in "
-                                    "full (own algorithmic bytes; latency-bound, not HBM-bound)") +
-                                   (", reference dtypes" if args.obs_format == "reference" else
-                                    ", COMPACT dtypes (uint8 planes, uint8 colour, int32 additional_info): own algorithmic bytes"),
-                       "l2": ("observation written per step (%.0f MB) exceeds L2 (126 MB)" % (b_alg * n_env / 1e6))
-                             if b_alg * n_env > 126e6 else
-                             ("observation per step (%.1f MB) fits in L2: writes may be absorbed by L2" % (b_alg * n_env / 1e6)),
-                       "parallelism": f"env-sharded x{world}, no data-path collective", "setup_s": round(t_build, 1),
-                       "ms_per_step_by_rank": [round(m / K, 5) for m in per_rank_ms]},
+            "config": workload_config(args, world, st),
+            "run": {"launch": ("one CUDA graph of the K steps" if graph is not None else "K steps launched from Python")
+                              + f" ({launches // K} kernel launches per step)",
+                    "obs_mode": ("full rewrite" if args.obs_update == "rewrite" else
+                                 "DELTA: persistent observation touched in place, envs that begin a new episode rewritten in "
+                                 "full (own algorithmic bytes; latency-bound, not HBM-bound)") +
+                                (", reference dtypes" if args.obs_format == "reference" else
+                                 ", COMPACT dtypes (uint8 planes, uint8 colour, int32 additional_info): own algorithmic bytes"),
+                    "setup_s": round(t_build, 1),
+                    "ms_per_step_by_rank": [round(m / K, 5) for m in per_rank_ms]},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": ncu_traffic(args.workload, n_env) if (args.obs_format == "reference" and args.obs_update == "rewrite") else None, "peak_source": peak_src,
@@ -433,7 +519,7 @@ def main():
         if not args.no_cpu_baseline and world == 1:
             # fresh interpreter: the worker pool must not be forked from a process holding a CUDA context
             res = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload",
-                                  args.workload, "--steps", "1", "--cpu-seconds", str(args.cpu_seconds)],
+                                  args.workload, "--steps", "2", "--warmup", "0", "--cpu-seconds", str(min(args.cpu_seconds, 8.0))],
                                  capture_output=True, text=True)
             try:
                 line["cpu_baseline"] = json.loads(res.stdout.strip().splitlines()[-1])["cpu_baseline"]

@@ -1,5 +1,9 @@
-"""Run the UNMODIFIED reference env (/root/reference/SPaRC_Gym/SPaRC_Gym.py) in this
-container, to pin the oracle and to generate the golden vectors under tests/golden/.
+"""TEST / BASELINE INFRASTRUCTURE (never imported by the product package).
+
+Run the UNMODIFIED reference env (SPaRC_Gym/SPaRC_Gym.py of tobiTKM/SPaRC-Gym) to pin the oracle, to generate the
+golden vectors under tests/golden/, and as the CPU arm of bench.py (`--impl reference`, `cpu_baseline.kind =
+"reference"`).  The reference tree is looked up in this order: $SPARC_REFERENCE_ROOT, /root/reference (the build
+container), baseline/_ref (a git-ignored install made by oracle/install_reference.py; it travels to the GPU box).
 
 The reference needs `gymnasium` and `pygame` (not installed, no network) and downloads
 its puzzles from the HF hub (SPaRC_Gym.py:77).  Recipe:
@@ -9,9 +13,8 @@ its puzzles from the HF hub (SPaRC_Gym.py:77).  Recipe:
   uses), `gymnasium.spaces`, `gymnasium.envs.registration` and `pygame`;
 * `datasets.load_dataset` monkey-patched to hand back our rows as a DataFrame.
 
-Nothing here is importable on the GPU box (`/root/reference` does not exist there):
-only `make_golden.py` and tests marked `reference` use it, and they skip when the
-reference is absent.
+On the GPU box `/root/reference` does not exist: only baseline/_ref can serve there, and only bench.py's CPU
+arm uses it (the `-m gpu` tests and smoke() never read the reference).
 """
 from __future__ import annotations
 
@@ -21,7 +24,22 @@ import types
 
 import numpy as np
 
-REFERENCE_ROOT = os.environ.get("SPARC_REFERENCE_ROOT", "/root/reference")
+REPO_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+INSTALL_ROOT = os.path.join(REPO_ROOT, "baseline", "_ref")
+
+
+def _has_engine(root):
+    return bool(root) and os.path.isfile(os.path.join(root, "SPaRC_Gym", "SPaRC_Gym.py"))
+
+
+def _find_root():
+    for root in (os.environ.get("SPARC_REFERENCE_ROOT"), "/root/reference", INSTALL_ROOT):
+        if _has_engine(root):
+            return root
+    return os.environ.get("SPARC_REFERENCE_ROOT", "/root/reference")
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def reference_available():

@@ -1,5 +1,5 @@
 """Generate the golden vectors in this directory by running the UNMODIFIED reference
-(/root/reference, imported through refharness.py).  Run once in the build container:
+(/root/reference, imported through oracle/refharness.py).  Run once in the build container:
 
     python tests/golden/make_golden.py
 
@@ -21,7 +21,8 @@ import sys
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-sys.path[:0] = [HERE, os.path.dirname(HERE), os.path.dirname(os.path.dirname(HERE))]
+sys.path[:0] = [HERE, os.path.dirname(HERE), os.path.dirname(os.path.dirname(HERE)),
+                os.path.join(os.path.dirname(os.path.dirname(HERE)), "oracle")]
 
 import refharness as rh                                     # noqa: E402
 from fuzzrows import SMALL_SHAPES, fuzz_actions, fuzz_row   # noqa: E402
