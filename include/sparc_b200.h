@@ -206,7 +206,10 @@ int sparc_env_create(SparcStore* store, int64_t n_envs, int traceback, int max_s
 int sparc_env_destroy(SparcEnv* env);
 
 /* replaces reset() (SG.py:1057-1108) with a CLEAN reset.  puzzle_idx_dev: int32[n_envs]
- * puzzle index per env, or NULL = keep the env's current puzzle (env i starts on i mod n_puzzles);
+ * puzzle index per env (taken modulo n_puzzles, Python style: -1 is the last puzzle; the indices live on
+ * the device, so a range error cannot be reported without a sync -- host wrappers check before uploading),
+ * or NULL = keep the env's current puzzle.  A freshly created env is already a clean reset on puzzle
+ * i mod n_puzzles.  Every entry point selects the store's device itself (cudaSetDevice).
  * mask_dev: uint8[n_envs] which envs to reset, or NULL = all.  Writes the observation of all envs. */
 int sparc_reset(SparcEnv* env, const int32_t* puzzle_idx_dev, const uint8_t* mask_dev,
                 const SparcStepOut* info_out, const SparcObsOut* obs, void* stream);

@@ -70,7 +70,7 @@ class StepOut(C.Structure):
 def build_library(force=False, verbose=False):
     """Compile csrc/sparc_b200.cu for sm_100a into csrc/libsparc_b200.so (in-tree)."""
     src = os.path.join(CSRC, "sparc_b200.cu")
-    deps = [src, os.path.join(CSRC, "sparc_core.cuh"), os.path.join(REPO_ROOT, "include", "sparc_b200.h")]
+    deps = [src, os.path.join(CSRC, "sparc_core.cuh"), os.path.join(CSRC, "sparc_val_warp.cuh"), os.path.join(REPO_ROOT, "include", "sparc_b200.h")]
     if not force and os.path.exists(LIB_PATH) and \
             os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(d) for d in deps):
         return LIB_PATH

@@ -8,8 +8,7 @@
 //   k_encode  state -> observation: a CTA owns a tile of 8 consecutive envs, stages their bit-packed planes
 //             in shared memory and expands them into the caller's int32/int64 tensors with coalesced
 //             16-byte streaming stores.  HBM-write bound: X*Y*(4P+4+8) bytes per env-step.
-// Small batches use the fused k_env (one launch, one tile per CTA).  k_env_ring is an opt-in persistent,
-// warp-specialised variant (mbarrier hand-off, optional TMA bulk stores) kept for experiments.
+// Small batches use the fused k_env (one launch, one tile per CTA).
 // The device functions themselves (dynamics, validator, encoder) live in sparc_core.cuh.
 #include <cuda_runtime.h>
 #include <stdio.h>
@@ -17,6 +16,7 @@
 #include <new>
 
 #include "sparc_core.cuh"
+#include "sparc_val_warp.cuh"
 
 #define CTA_THREADS 128
 #ifndef SPARC_MINBLOCKS          // resident CTAs per SM the register allocator must allow.  8 -> 64
@@ -37,7 +37,7 @@ static int fail(int code, const char* fmt, const char* detail = "") {
 struct SparcStore {
     int device;
     StoreDev d;
-    void* blocks[9];
+    void* blocks[10];
     int plane_ids[SPARC_MAX_PLANES];
 };
 
@@ -59,8 +59,6 @@ struct SparcEnv {
     uint32_t* rq;            // [n_envs]
     int val_grid;            // CTAs of k_val beside the full-rewrite encoder
     int val_grid_delta;      // ... when nothing but k_encode_list runs beside it (update = SPARC_OBS_DELTA)
-    int ring_grid;           // >0: use k_env_ring with this many persistent CTAs (one per SM)
-    unsigned int* sched;     // [2] tile counter + finished-producer counter of k_env_ring
     int64_t launches;
     uint8_t* act_stage;      // device staging for the *_host call
     float* rew_stage;
@@ -78,7 +76,6 @@ extern __shared__ __align__(128) uint32_t smem[];
 #define SPARC_STAT_ROWS 1024
 #endif
 __device__ __forceinline__ void reduce_stats(const KParams& p, bool have, const unsigned long long* my) {
-#ifndef DYN_NO_STATS      /* timing experiment only */
     // steps / episodes / solved / failed / truncated / rules_pass are 0-or-1 per env: ballots, not shuffle sums;
     // only a warp in which an episode ended (40 % of them at 1.6 % per env) reduces anything beyond `steps`
     const unsigned full = 0xffffffffu;
@@ -106,7 +103,6 @@ __device__ __forceinline__ void reduce_stats(const KParams& p, bool have, const 
         if (ret) atomicAdd(row + SPARC_STAT_RETURN_CENTS, (unsigned long long)ret);
         atomicAdd(row + SPARC_STAT_LENGTH, len);
     }
-#endif
 }
 
 // ---- simple kernel: one CTA = one tile (small batches: every CTA is resident at once) ----------
@@ -172,28 +168,24 @@ __global__ void __launch_bounds__(CTA_THREADS, DYN_MINBLOCKS) k_dyn(const KParam
     if (p.mode == 0) reduce_stats(p, have_stats, my_stats);
 }
 
-// deferred terminal validation: a small grid walks the queue k_dyn filled, one snapshot per thread.
-// (A warp-per-snapshot variant -- every lane floods from a different rule cell, the first cell of
-// each region checks its rules -- was measured: it bounds the many-region tail but doubles the
-// mean, because typical terminal states have 1-3 regions and 36 cells need two flood rounds:
-// k_val 47 -> 95 us, step 0.205 -> 0.230 ms.  Kept serial.)
+// deferred terminal validation: the grid walks the queue k_dyn filled, one snapshot per WARP (validate_warp in
+// sparc_val_warp.cuh: boards one word per lane, region rules one colour / one shape slot per lane, the exact-fit search
+// split over the lanes).  Round 1 ran one snapshot per thread: 10.7 us of lone dependent chain each, 7.6 of 32 lanes
+// active, the kernel as long as its slowest thread (24-39 us typical, 408 us at worst: profiles/r1_valprof.txt).
 __global__ void __launch_bounds__(CTA_THREADS) k_val(const KParams p) {
     const uint32_t count = *p.vq_count;
-    unsigned long long pass = 0;
-    // Snapshots are dealt out warp by warp (slot s -> warp s mod nwarps), not thread by thread: every snapshot is
-    // a different puzzle and path, so the lanes of a warp diverge and run one after the other -- the fewer
-    // snapshots share a warp, the shorter the kernel.
+    const int lane = threadIdx.x & 31;
     const uint32_t nwarps = gridDim.x * (CTA_THREADS / 32);
-    const uint32_t warp = blockIdx.x * (CTA_THREADS / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-#ifdef VAL_DENSE      /* experiment: the old thread-by-thread mapping */
-    for (uint32_t slot = blockIdx.x * CTA_THREADS + threadIdx.x; slot < count; slot += gridDim.x * CTA_THREADS)
-#else
-    for (uint32_t slot = lane * nwarps + warp; slot < count; slot += 32 * nwarps)
-#endif
-        pass += (unsigned long long)validate_queued(p, slot);
-#pragma unroll
-    for (int off = 16; off; off >>= 1) pass += __shfl_down_sync(0xffffffffu, pass, off);
-    if ((threadIdx.x & 31) == 0 && pass) atomicAdd(p.sd.stats + SPARC_STAT_RULES_PASS, pass);
+    unsigned long long pass = 0;
+    for (uint32_t slot = blockIdx.x * (CTA_THREADS / 32) + (threadIdx.x >> 5); slot < count; slot += nwarps) {
+        const uint32_t qw = lane < SPARC_VQ_WORDS ? p.vq[(size_t)slot * SPARC_VQ_WORDS + lane] : 0u;   // 48 contiguous bytes
+        const int f = validate_warp(p.st, qw, lane) | SPARC_RULE_VALID;
+        if (lane == 0) {
+            if (p.out.rule_flags_dev) p.out.rule_flags_dev[qw] = (uint16_t)f;                          // word 0 = env
+            pass += (f & SPARC_RULE_ALL) != 0;
+        }
+    }
+    if (lane == 0 && pass) atomicAdd(p.sd.stats + SPARC_STAT_RULES_PASS, pass);
     __syncthreads();                                             // every thread of the CTA has read `count`
     if (threadIdx.x == 0) {                                      // last CTA out empties the queue for the next step
         __threadfence();
@@ -201,12 +193,6 @@ __global__ void __launch_bounds__(CTA_THREADS) k_val(const KParams p) {
     }
 }
 
-// (k_val_g8 -- eight lanes per snapshot, lane l owning word l of every 16-stride board: a flood sweep is one row_fill,
-// two shuffles and a ballot, the per-region rules run redundantly on the 8 lanes -- was written, verified against
-// k_val on 40 k terminal states, and measured: no faster with one round per group (delta step 0.0514 vs 0.0510 ms at
-// 148 CTAs), twice as slow at 32 CTAs (4 rounds: k_dyn + k_val 78 vs 46 us).  The sweep's dependent chain is as long
-// with one word per lane as with eight words of instruction-level parallelism in one lane, so the instruction count
-// it saves was not the limit.  Removed; profiles/r1_ab_val_g8.txt.)
 #ifndef ENC_THREADS
 #define ENC_THREADS 128
 #endif
@@ -221,10 +207,6 @@ __global__ void __launch_bounds__(ENC_THREADS, ENC_MINBLOCKS) k_encode(const KPa
     const int nE = (int)min((long long)p.tile, hi - env0);
     uint32_t* head = smem;
     uint32_t* flats = smem + tile_head_words(p.tile);
-#ifdef ENC_SKIP_STAGE1      /* timing experiment only (wrong output): how fast is the expand loop alone? */
-    if (tid < nE) head[p.tile * SPARC_DYN_STRIDE + tid] = 0;
-    __syncthreads();
-#else
     if (tid < nE) {
         EnvRegs e;
         load_env(e, p.sd, st, p.cfg.n_envs, env0 + tid);
@@ -237,7 +219,6 @@ __global__ void __launch_bounds__(ENC_THREADS, ENC_MINBLOCKS) k_encode(const KPa
     __syncthreads();
     encode_tile_stage1b<FMT>(st, head, flats, p.tile, nE, p.obs, tid, ENC_THREADS);
     __syncthreads();
-#endif
     encode_tile_stage2<FMT>(st, head, flats, p.tile, nE, env0, p.obs, tid, ENC_THREADS);
 }
 
@@ -276,233 +257,6 @@ __global__ void __launch_bounds__(ENC_THREADS) k_encode_list(const KParams p) {
     }
 }
 
-// ---- ring kernel: one persistent, warp-specialised CTA per SM -------------------------------------
-// RING_PROD producer warps each own one shared-memory slot.  A producer takes the next tile of
-// 32 envs from a global counter, runs the latency-bound part (dynamics, terminal validation,
-// autoreset: one env per lane) and packs the tile's observation into the slot's flat bit strings;
-// RING_CONS consumer warps visit the slots round-robin and do nothing but turn bit strings into
-// coalesced 16-byte streaming stores.  Hand-off is by mbarriers (full / empty per slot).
-//
-// Why one fat CTA per SM instead of many thin ones: (1) the store path of an SM is only busy
-// while some warp is in the expand loop, so the dependent-load chains must run *beside* it, not
-// in front of it; (2) HBM write efficiency depends on how much memory is being written at once --
-// tools/wpattern.cu measures 7.2 TB/s when the chip-wide window of open tiles is ~40 MB and
-// 6.5 TB/s at 166-330 MB (1184 thin CTAs x 140-281 KB); 148 CTAs x 281 KB keeps it at 41 MB.
-#ifndef RING_PROD
-#define RING_PROD 8
-#endif
-#ifndef RING_CONS
-#define RING_CONS 8
-#endif
-#define RING_THREADS ((RING_PROD + RING_CONS) * 32)
-#define RING_TILE 32
-#define RING_END 0xFFFFFFFFu
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    do {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    } while (!ok);
-}
-
-// ---- consumer side of the ring kernel: expand into a shared staging block, then hand the block to
-// the TMA engine (cp.async.bulk shared -> global).  Global stores issued through the LSU
-// (st.global) fill the SM's load/store queue and every load of the producer warps queues up behind
-// them (measured: the producers' dependent-load chains ran ~5x slower next to an st.global stream);
-// bulk stores keep the LSU free for the producers.
-#define STAGE_CHUNKS 256                         // 16-byte chunks per staging block (4 KB)
-#define STAGE_WORDS (STAGE_CHUNKS * 4)
-__device__ __forceinline__ void tma_store(void* gdst, const void* ssrc, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
-__device__ __forceinline__ void tma_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
-__device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-// One warp writes its share of a stream: blocks of STAGE_CHUNKS chunks, block b by warp b mod nw.
-// `fill(c)` returns the 16 bytes of chunk c.  stage: 2 x STAGE_WORDS words private to the warp.
-template <class Fill>
-__device__ __forceinline__ void stream_blocks(char* gbase, int nchunks, int wc, int nw, int lane, uint32_t* stage,
-                                              uint32_t& phase, const Fill& fill) {
-    for (int b0 = wc * STAGE_CHUNKS; b0 < nchunks; b0 += nw * STAGE_CHUNKS) {
-        uint32_t* buf = stage + (phase & 1u) * STAGE_WORDS;
-        if (lane == 0) tma_wait_read_1();                     // the block sent two rounds ago has left this buffer
-        __syncwarp();
-        const int cnt = min(STAGE_CHUNKS, nchunks - b0);
-#pragma unroll
-        for (int it = 0; it < STAGE_CHUNKS / 32; it++) {
-            const int q = it * 32 + lane;
-            if (q < cnt) reinterpret_cast<int4*>(buf)[q] = fill(b0 + q);
-        }
-        fence_async_smem();
-        __syncwarp();
-        if (lane == 0) tma_store(gbase + (size_t)b0 * 16, buf, (uint32_t)cnt * 16u);
-        phase++;
-    }
-}
-
-__device__ __forceinline__ void ring_expand_tile(const StoreDev& st, const uint32_t* head, const uint32_t* flats, int nE,
-                                                 long long env0, const SparcObsOut& obs, int wc, int nw, int lane,
-                                                 uint32_t* stage, uint32_t& phase) {
-    const uint32_t* tile_puzzle = head + RING_TILE * SPARC_DYN_STRIDE;
-    const uint32_t* rb = flats;
-    const uint32_t* rc = rb + RING_TILE * (st.W + 2);
-    const uint32_t* rz = rc + RING_TILE * (st.Wc + 2);
-    if (obs.base_dev) {
-        const int L = st.L, Ws = st.W + 2, total = nE * L;
-        int32_t* out = static_cast<int32_t*>(obs.base_dev) + (size_t)env0 * L;
-        stream_blocks(reinterpret_cast<char*>(out), total >> 2, wc, nw, lane, stage, phase, [&](int c) {
-            const uint32_t n = row_fetch(rb, 4u * (uint32_t)c, L, Ws, st.inv_L);
-            return make_int4(n & 1, (n >> 1) & 1, (n >> 2) & 1, (n >> 3) & 1);
-        });
-        if (wc == 0) for (int e = (total & ~3) + lane; e < total; e += 32) out[e] = row_fetch(rb, (uint32_t)e, L, Ws, st.inv_L) & 1u;
-    }
-    if (obs.color_dev) {
-        const int L = 4 * st.S, Ws = st.Wc + 2, total = nE * st.S;
-        int32_t* out = static_cast<int32_t*>(obs.color_dev) + (size_t)env0 * st.S;
-        stream_blocks(reinterpret_cast<char*>(out), total >> 2, wc, nw, lane, stage, phase, [&](int c) {
-            const uint32_t n = row_fetch(rc, 16u * (uint32_t)c, L, Ws, st.inv_4S);
-            return make_int4(n & 15, (n >> 4) & 15, (n >> 8) & 15, (n >> 12) & 15);
-        });
-        if (wc == 0) for (int e = (total & ~3) + lane; e < total; e += 32) out[e] = row_fetch(rc, 4u * (uint32_t)e, L, Ws, st.inv_4S) & 15u;
-    }
-    if (obs.info_dev) {
-        const int S = st.S, Ws = st.nv + 2, total = nE * S;
-        int64_t* out = static_cast<int64_t*>(obs.info_dev) + (size_t)env0 * S;
-        stream_blocks(reinterpret_cast<char*>(out), total >> 1, wc, nw, lane, stage, phase, [&](int c) {
-            const uint32_t e0 = 2u * (uint32_t)c;
-            const uint32_t m = row_fetch(rz, e0, S, Ws, st.inv_S) & 3u;
-            int32_t a = 0, b = 0;
-            if (m) {
-                const int j = (int)__umulhi(e0, st.inv_S), r = (int)e0 - j * S;
-                if (m & 1) a = __ldg(st.info + (size_t)tile_puzzle[j] * S + r);
-                if (m & 2) {
-                    const int j2 = (r + 1 >= S) ? j + 1 : j, r2 = (r + 1 >= S) ? 0 : r + 1;
-                    b = __ldg(st.info + (size_t)tile_puzzle[j2] * S + r2);
-                }
-            }
-            return make_int4(a, a >> 31, b, b >> 31);
-        });
-        if ((total & 1) && wc == 0 && lane == 0) {
-            const int e = total - 1, jj = e / S, rr = e - jj * S;
-            out[e] = __ldg(st.info + (size_t)tile_puzzle[jj] * S + rr);
-        }
-    }
-}
-
-__host__ __device__ inline int ring_slot_words(const StoreDev& st) {
-    return (tile_head_words(RING_TILE) + 1 + tile_flat_words(st, RING_TILE) + 3) & ~3;   // keeps the staging blocks 16-byte aligned
-}
-
-__global__ void __launch_bounds__(RING_THREADS, 1) k_env_ring(const KParams p, unsigned int* sched) {
-    const StoreDev& st = p.st;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const long long n = p.cfg.n_envs;
-    const unsigned ntiles = (unsigned)((n + RING_TILE - 1) / RING_TILE);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem);              // [RING_PROD]
-    uint64_t* empty = full + RING_PROD;                              // [RING_PROD]
-    uint32_t* slots = smem + 4 * RING_PROD;
-    const int slot_words = ring_slot_words(st);
-    const int hw = tile_head_words(RING_TILE);
-    if (tid == 0) {
-        for (int w = 0; w < RING_PROD; w++) { mbar_init(full + w, 1); mbar_init(empty + w, RING_CONS); }
-    }
-    __syncthreads();
-#ifdef RING_PROFILE
-    long long t_wait = 0, t_a = 0, t_b = 0, t_c = 0, t0;
-#define TICK() (t0 = clock64())
-#define TOCK(acc) (acc += clock64() - t0)
-#else
-#define TICK() ((void)0)
-#define TOCK(acc) ((void)0)
-#endif
-    if (warp < RING_PROD) {                                          // ------------------- producers
-        uint32_t* head = slots + (size_t)warp * slot_words;
-        uint32_t* flats = head + hw + 1;
-        for (uint32_t r = 0;; r++) {
-            TICK();
-            if (r > 0) mbar_wait(empty + warp, (r - 1) & 1);         // the consumers drained round r-1
-            TOCK(t_wait);
-            unsigned t = 0;
-            if (lane == 0) t = atomicAdd(sched, 1u);
-            t = __shfl_sync(0xffffffffu, t, 0);
-            if (t >= ntiles) {
-                if (lane == 0) { head[hw] = RING_END; mbar_arrive(full + warp); }
-                break;
-            }
-            const long long env0 = (long long)t * RING_TILE;
-            const int nE = (int)min((long long)RING_TILE, n - env0);
-            EnvRegs e;
-            unsigned long long my_stats[SPARC_N_STATS];
-            bool have_stats = false;
-            TICK();
-            if (lane < nE) {
-                prefetch_static(st, p.sd.core[4 * (env0 + lane)]);   // encoder inputs arrive while the dynamics run
-                have_stats = phase_a(p, env0 + lane, e, head + lane * SPARC_DYN_STRIDE, my_stats);
-                head[RING_TILE * SPARC_DYN_STRIDE + lane] = e.puzzle;
-                write_dyn(st, head, lane, e);
-            }
-            if (p.mode == 0) reduce_stats(p, have_stats, my_stats);
-            __syncwarp();
-            TOCK(t_a);
-            TICK();
-            encode_tile_stage1a(st, head, flats, RING_TILE, nE, p.obs, lane, 32);
-            __syncwarp();
-            encode_tile_stage1b(st, head, flats, RING_TILE, nE, p.obs, lane, 32);
-            __syncwarp();
-            TOCK(t_b);
-            if (lane == 0) { head[hw] = t; mbar_arrive(full + warp); }   // release: slot contents visible
-        }
-#ifdef RING_PROFILE
-        if (lane == 0) { atomicAdd((unsigned long long*)(sched + 2), (unsigned long long)t_wait); atomicAdd((unsigned long long*)(sched + 4), (unsigned long long)t_a); atomicAdd((unsigned long long*)(sched + 6), (unsigned long long)t_b); }
-#endif
-        if (lane == 0) {                                             // last producer of the grid re-arms the scheduler
-            __threadfence();
-            if (atomicAdd(sched + 1, 1u) == gridDim.x * RING_PROD - 1) { sched[0] = 0; sched[1] = 0; __threadfence(); }
-        }
-    } else {                                                         // ------------------- consumers
-        const int wc = warp - RING_PROD;
-        uint32_t* stage = slots + (size_t)RING_PROD * slot_words + (size_t)wc * 2 * STAGE_WORDS;
-        uint32_t parity = 0, done = 0, stage_phase = 0;
-        const uint32_t all = (1u << RING_PROD) - 1u;
-        for (int w = 0; done != all; w = (w + 1 == RING_PROD) ? 0 : w + 1) {
-            if ((done >> w) & 1u) continue;
-            const uint32_t* head = slots + (size_t)w * slot_words;
-            TICK();
-            mbar_wait(full + w, (parity >> w) & 1u);
-            TOCK(t_wait);
-            parity ^= 1u << w;
-            const uint32_t t = head[hw];
-            if (t == RING_END) { done |= 1u << w; continue; }
-            const long long env0 = (long long)t * RING_TILE;
-            const int nE = (int)min((long long)RING_TILE, n - env0);
-            TICK();
-#ifdef RING_TMA_STORE
-            ring_expand_tile(st, head, head + hw + 1, nE, env0, p.obs, wc, RING_CONS, lane, stage, stage_phase);
-#else
-            (void)stage; (void)stage_phase;
-            encode_tile_stage2(st, head, head + hw + 1, RING_TILE, nE, env0, p.obs, tid - RING_PROD * 32, RING_CONS * 32);
-#endif
-            __syncwarp();
-            TOCK(t_c);
-            if (lane == 0) mbar_arrive(empty + w);                   // (the rows were read into the staging blocks)
-        }
-        if (lane == 0) tma_wait_all();                               // bulk stores must drain before the CTA retires
-#ifdef RING_PROFILE
-        if (lane == 0) { atomicAdd((unsigned long long*)(sched + 8), (unsigned long long)t_wait); atomicAdd((unsigned long long*)(sched + 10), (unsigned long long)t_c); }
-#endif
-    }
-}
-
 // stand-alone validator (SG.py:941-950) for sparc_validate: one env per thread
 __global__ void __launch_bounds__(CTA_THREADS) k_validate(const StoreDev st, const StateDev sd, long long n,
                                                           const uint8_t* mask, uint16_t* flags, int8_t* region_map,
@@ -524,11 +278,14 @@ __global__ void __launch_bounds__(CTA_THREADS) k_validate(const StoreDev st, con
     if (flags) flags[i] = (uint16_t)(f | SPARC_RULE_VALID);
 }
 
-__global__ void k_init_state(StateDev sd, long long n, int n_puzzles) {
+// a fresh env is a clean reset on puzzle i mod pool: stepping, encoding or validating before the first sparc_reset
+// works on a state a puzzle can produce (start node visited, agent on the start)
+__global__ void k_init_state(StoreDev st, StateDev sd, long long n) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    sd.core[4 * i + 0] = (uint32_t)(i % n_puzzles);
-    sd.core[4 * i + 1] = 0; sd.core[4 * i + 2] = 0; sd.core[4 * i + 3] = 0;
+    EnvRegs e;
+    env_reset(e, st, (uint32_t)(i % st.n_puzzles));
+    store_env(e, sd, st, n, i);
 }
 
 __global__ void k_read_stats(unsigned long long* stats, long long* out, int clear) {     // <<<1, 32 * SPARC_N_STATS>>>
@@ -600,6 +357,32 @@ int sparc_store_create(const SparcStoreDesc* desc, int device, SparcStore** out)
         sparc_store_destroy(s);
         return rc;
     }
+    {   // validator records of k_val (layout: sparc_val_warp.cuh), assembled from the arrays above
+        uint32_t* vr = new (std::nothrow) uint32_t[n * SPARC_VREC_WORDS];
+        if (!vr) { sparc_store_destroy(s); return fail(SPARC_E_NOMEM, "out of host memory%s"); }
+        static const int nb_of[9] = {SPARC_NB_GAPS16, SPARC_NB_CELL16, SPARC_NB_VALID16, SPARC_NB_DOT16, SPARC_NB_TRI1,
+                                     SPARC_NB_TRI2, SPARC_NB_TRI3, SPARC_NB_TRI4, SPARC_NB_TRIBAD};
+        for (size_t i = 0; i < n; i++) {
+            const SparcPuzzleHeader& h = desc->headers[i];
+            const uint32_t* nb = desc->node_boards + i * SPARC_N_NODE_BOARDS * 8;
+            const uint64_t* cb = desc->cell_boards + i * SPARC_N_CELL_BOARDS;
+            uint64_t anycol = 0;
+            for (int c = 0; c < 8; c++) anycol |= cb[SPARC_CB_COLOR1 + c];
+            for (int k = 0; k < 8; k++) {
+                uint32_t* r = vr + (i * 8 + k) * SPARC_VREC_ROW_WORDS;
+                for (int b = 0; b < 9; b++) r[b] = nb[nb_of[b] * 8 + k];
+                r[9] = (uint32_t)h.X | ((uint32_t)h.Y << 8) | ((uint32_t)h.start_x << 16) | ((uint32_t)h.start_y << 24);
+                r[10] = (uint32_t)h.target_x | ((uint32_t)h.target_y << 8) | ((uint32_t)h.n_shapes << 16) | ((uint32_t)h.flags << 24);
+                r[11] = h.shape_off;
+                const uint64_t cells[6] = {cb[SPARC_CB_STAR], cb[SPARC_CB_SQUARE], cb[SPARC_CB_SYM1], cb[SPARC_CB_SYM2],
+                                           cb[SPARC_CB_COLOR1 + k], anycol};
+                for (int c = 0; c < 6; c++) { r[12 + 2 * c] = (uint32_t)cells[c]; r[13 + 2 * c] = (uint32_t)(cells[c] >> 32); }
+            }
+        }
+        rc = upload(vr, n * SPARC_VREC_WORDS, &d.vrec, &s->blocks[9]);
+        delete[] vr;
+        if (rc) { sparc_store_destroy(s); return rc; }
+    }
     *out = s;
     return SPARC_OK;
 }
@@ -611,6 +394,11 @@ int sparc_store_destroy(SparcStore* s) {
     delete s;
     return SPARC_OK;
 }
+
+// uint8 streams stay 16-byte aligned only when every tile starts at a multiple of 16 envs
+static int compact_tile(int t) { t = (t + 15) / 16 * 16; return t > CTA_THREADS ? CTA_THREADS : t; }
+
+extern "C" int sparc_env_destroy(SparcEnv* e);
 
 static int pick_tile(int64_t n) {
     const char* env = getenv("SPARC_TILE");
@@ -633,16 +421,6 @@ int sparc_env_create(SparcStore* store, int64_t n_envs, int traceback, int max_s
     e->cfg.n_envs = n_envs; e->cfg.traceback = traceback != 0; e->cfg.max_steps = max_steps;
     e->cfg.autoreset = autoreset_mode; e->cfg.stride = puzzle_stride; e->cfg.validate_mode = validate_mode;
     e->tile = pick_tile(n_envs);
-    {   // tiles above ~100 envs need more than the default 48 KB of dynamic shared memory
-        const size_t shmem = (size_t)(tile_head_words(e->tile) + tile_flat_words(store->d, e->tile)) * sizeof(uint32_t);
-        if (shmem > 48 * 1024) {
-            cudaError_t ae = cudaFuncSetAttribute(k_env<SPARC_OBS_REFERENCE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem);
-            if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_env<SPARC_OBS_COMPACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem);
-            if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_encode<SPARC_OBS_REFERENCE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem);
-            if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_encode<SPARC_OBS_COMPACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem);
-            if (ae != cudaSuccess) { delete e; return fail(SPARC_E_CUDA, "k_env shared memory: %s", cudaGetErrorString(ae)); }
-        }
-    }
     {   // big batches: the k_dyn || k_encode pipeline
         const char* pe = getenv("SPARC_SPLIT");                // chunks; 0 = fused k_env; unset = automatic
         int nc = pe ? atoi(pe) : (n_envs >= 8192 ? 1 : 0);    // measured crossover with the fused k_env: ~6 k envs;
@@ -651,6 +429,19 @@ int sparc_env_create(SparcStore* store, int64_t n_envs, int traceback, int max_s
         const char* te = getenv("SPARC_ENC_TILE");
         e->enc_tile = te ? atoi(te) : 8;
         if (e->enc_tile < 4 || e->enc_tile > ENC_THREADS || e->enc_tile % 4) e->enc_tile = 8;
+        {   // every tile a launch can pick (fused / split, reference / compact) must fit the kernels' dynamic shared memory
+            int tmax = e->tile > e->enc_tile ? e->tile : e->enc_tile;
+            if (tmax < 32) tmax = 32;                               // compact default
+            tmax = compact_tile(tmax);
+            const size_t shmem = (size_t)(tile_head_words(tmax) + tile_flat_words(store->d, tmax)) * sizeof(uint32_t);
+            if (shmem > 48 * 1024) {
+                cudaError_t ae = cudaFuncSetAttribute(k_env<SPARC_OBS_REFERENCE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem);
+                if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_env<SPARC_OBS_COMPACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem);
+                if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_encode<SPARC_OBS_REFERENCE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem);
+                if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_encode<SPARC_OBS_COMPACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem);
+                if (ae != cudaSuccess) { sparc_env_destroy(e); return fail(SPARC_E_CUDA, "dynamic shared memory: %s", cudaGetErrorString(ae)); }
+            }
+        }
         if (nc > 0) {
             int lo_p = 0, hi_p = 0;
             cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p);
@@ -669,30 +460,16 @@ int sparc_env_create(SparcStore* store, int64_t n_envs, int traceback, int max_s
                 int dev_sms = 0;
                 cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, store->device);
                 (void)dev_sms;
-                e->val_grid = 32;              // x128 threads; a small grid disturbs the co-running encoder least (measured)
+                e->val_grid = 148;             // x4 warps = snapshots in flight beside the full-rewrite encoder
                 const char* ve = getenv("SPARC_VAL_GRID");
                 if (ve && atoi(ve) > 0) e->val_grid = atoi(ve);
-                e->val_grid_delta = 148;       // measured, delta step: 32 CTAs 0.0528, 64 0.0512, 148 0.0502, 296 0.0505 ms
+                e->val_grid_delta = 592;       // a warp per snapshot for ~2,400 snapshots (1.6 % of 131,072 envs end per step)
                 const char* vd = getenv("SPARC_VAL_GRID_DELTA");
                 if (vd && atoi(vd) > 0) e->val_grid_delta = atoi(vd);
 
             }
-            if (se != cudaSuccess) { delete e; return fail(SPARC_E_CUDA, "side stream / queue: %s", cudaGetErrorString(se)); }
+            if (se != cudaSuccess) { sparc_env_destroy(e); return fail(SPARC_E_CUDA, "side stream / queue: %s", cudaGetErrorString(se)); }
             e->split_chunks = nc;
-        }
-    }
-    {   // opt-in: the ring kernel, one persistent CTA per SM
-        int dev_sms = 0;
-        cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, store->device);
-        const char* pe = getenv("SPARC_RING");
-        const int want = pe ? atoi(pe) : -1;                  // 0 = never, 1 = always, unset = automatic
-        const size_t shmem = (size_t)(4 * RING_PROD + RING_PROD * ring_slot_words(store->d) + RING_CONS * 2 * STAGE_WORDS) * sizeof(uint32_t);
-        const int64_t ntiles = (n_envs + RING_TILE - 1) / RING_TILE;
-        (void)ntiles;
-        if (want == 1) {      // opt-in: measured on par with the one-tile-per-CTA kernel so far (kernel notes)
-            cudaError_t ae = cudaFuncSetAttribute(k_env_ring, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem);
-            if (ae != cudaSuccess) { delete e; return fail(SPARC_E_CUDA, "ring kernel shared memory: %s", cudaGetErrorString(ae)); }
-            e->ring_grid = (int)(ntiles < dev_sms ? ntiles : dev_sms);
         }
     }
     const size_t n = (size_t)n_envs;
@@ -703,7 +480,6 @@ int sparc_env_create(SparcStore* store, int64_t n_envs, int traceback, int max_s
     alloc((void**)&e->s.ep_ret, n * 4);
     if (traceback) alloc((void**)&e->s.moves, n * SPARC_MOVE_WORDS * 4);
     alloc((void**)&e->s.stats, (size_t)SPARC_STAT_ROWS * SPARC_N_STATS * 8);
-    alloc((void**)&e->sched, 16 * sizeof(unsigned int));   // [2..] cycle counters when built with -DRING_PROFILE
     alloc((void**)&e->rq_count, 2 * sizeof(uint32_t));
     alloc((void**)&e->rq, n * sizeof(uint32_t));
     alloc((void**)&e->act_stage, n);
@@ -711,7 +487,7 @@ int sparc_env_create(SparcStore* store, int64_t n_envs, int traceback, int max_s
     alloc((void**)&e->term_stage, n);
     alloc((void**)&e->trunc_stage, n);
     if (err != cudaSuccess) { sparc_env_destroy(e); return fail(SPARC_E_CUDA, "cudaMalloc: %s", cudaGetErrorString(err)); }
-    k_init_state<<<(unsigned)((n + 255) / 256), 256>>>(e->s, n_envs, store->d.n_puzzles);
+    k_init_state<<<(unsigned)((n + 255) / 256), 256>>>(store->d, e->s, n_envs);
     CU(cudaGetLastError());
     CU(cudaDeviceSynchronize());
     *out = e;
@@ -721,7 +497,7 @@ int sparc_env_create(SparcStore* store, int64_t n_envs, int traceback, int max_s
 int sparc_env_destroy(SparcEnv* e) {
     if (!e) return SPARC_OK;
     cudaSetDevice(e->store->device);
-    void* ptrs[] = {e->s.core, e->s.vis, e->s.ep_ret, e->s.moves, e->s.stats, e->sched, e->vq_count, e->vq, e->rq_count, e->rq, e->act_stage, e->rew_stage, e->term_stage, e->trunc_stage};
+    void* ptrs[] = {e->s.core, e->s.vis, e->s.ep_ret, e->s.moves, e->s.stats, e->vq_count, e->vq, e->rq_count, e->rq, e->act_stage, e->rew_stage, e->term_stage, e->trunc_stage};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (e->side) cudaStreamDestroy(e->side);
     if (e->ev_start) cudaEventDestroy(e->ev_start);
@@ -735,12 +511,12 @@ int sparc_env_destroy(SparcEnv* e) {
 }
 
 static int launch_env(SparcEnv* e, KParams& p, void* stream) {
+    CU(cudaSetDevice(e->store->device));          // raw C-ABI callers on multi-GPU hosts need not do it themselves
     p.st = e->store->d; p.sd = e->s; p.cfg = e->cfg; p.tile = e->tile;
     const int64_t n = e->cfg.n_envs;
     if (p.obs.format != SPARC_OBS_REFERENCE && p.obs.format != SPARC_OBS_COMPACT) return fail(SPARC_E_ARG, "bad observation format%s");
-    // uint8 streams stay 16-byte aligned only when every tile starts at a multiple of 16 envs
     const bool compact = p.obs.format == SPARC_OBS_COMPACT;
-    if (compact && p.tile < 16) p.tile = 16;
+    if (compact) p.tile = compact_tile(p.tile);
     const unsigned ntiles = (unsigned)((n + p.tile - 1) / p.tile);
     if (p.obs.update != SPARC_OBS_REWRITE && p.obs.update != SPARC_OBS_DELTA) return fail(SPARC_E_ARG, "bad observation update mode%s");
     if (p.mode == 1) p.obs.update = SPARC_OBS_REWRITE;                   // a reset always writes in full
@@ -752,7 +528,7 @@ static int launch_env(SparcEnv* e, KParams& p, void* stream) {
         const int64_t per = ((n + nc - 1) / nc + 127) / 128 * 128;       // chunk boundaries stay 16-B aligned in every stream
         // compact: 32 envs = 81 KB per CTA unless SPARC_ENC_TILE says otherwise (measured with plain-row staging,
         // k_encode / step in us: 16 -> 59.7 / 86.7, 32 -> 59.8 / 82.3, 48 -> 62.6 / 83.8, 64 -> 67.9 / 87.2, 96 -> 80.7 / 95.5)
-        p.tile = compact ? ((getenv("SPARC_ENC_TILE") && e->enc_tile % 16 == 0) ? e->enc_tile : 32) : e->enc_tile;
+        p.tile = compact ? (getenv("SPARC_ENC_TILE") ? compact_tile(e->enc_tile) : 32) : e->enc_tile;
         const size_t shmem = (size_t)(tile_head_words(p.tile) + tile_flat_words(p.st, p.tile)) * sizeof(uint32_t);
         cudaStream_t sd = nc > 1 ? e->side : s0;                         // one chunk: plain back-to-back launches
         const bool defer = p.mode == 0 && e->vq && e->cfg.validate_mode == SPARC_VALIDATE_TERMINAL;
@@ -819,13 +595,7 @@ static int launch_env(SparcEnv* e, KParams& p, void* stream) {
         CU(cudaGetLastError());
         return SPARC_OK;
     }
-    if (e->ring_grid > 0) {
-        if (p.obs.update == SPARC_OBS_DELTA) return fail(SPARC_E_ARG, "the ring kernel (SPARC_RING=1) rewrites the observation in full only%s");
-        if (compact) return fail(SPARC_E_ARG, "the ring kernel (SPARC_RING=1) writes the reference format only%s");
-        p.tile = RING_TILE;
-        const size_t shmem = (size_t)(4 * RING_PROD + RING_PROD * ring_slot_words(p.st) + RING_CONS * 2 * STAGE_WORDS) * sizeof(uint32_t);
-        k_env_ring<<<(unsigned)e->ring_grid, RING_THREADS, shmem, (cudaStream_t)stream>>>(p, e->sched);
-    } else {
+    {
         const size_t shmem = (size_t)(tile_head_words(p.tile) + tile_flat_words(p.st, p.tile)) * sizeof(uint32_t);
         if (compact) k_env<SPARC_OBS_COMPACT><<<ntiles, CTA_THREADS, shmem, (cudaStream_t)stream>>>(p);
         else k_env<SPARC_OBS_REFERENCE><<<ntiles, CTA_THREADS, shmem, (cudaStream_t)stream>>>(p);
@@ -857,12 +627,13 @@ int sparc_step(SparcEnv* e, const void* actions_dev, int action_dtype, const Spa
 
 int sparc_encode(SparcEnv* e, const SparcObsOut* obs, void* stream) {
     if (!e || !obs) return fail(SPARC_E_ARG, "null argument%s");
+    CU(cudaSetDevice(e->store->device));
     KParams p; memset(&p, 0, sizeof(p));
     p.st = e->store->d; p.sd = e->s; p.cfg = e->cfg; p.obs = *obs;
     const int64_t n = e->cfg.n_envs;
     if (obs->format != SPARC_OBS_REFERENCE && obs->format != SPARC_OBS_COMPACT) return fail(SPARC_E_ARG, "bad observation format%s");
     p.tile = e->split_chunks > 0 ? e->enc_tile : (e->tile <= ENC_THREADS ? e->tile : 32);
-    if (obs->format == SPARC_OBS_COMPACT && p.tile < 32) p.tile = 32;
+    if (obs->format == SPARC_OBS_COMPACT) p.tile = p.tile < 32 ? 32 : compact_tile(p.tile);
     const size_t shmem = (size_t)(tile_head_words(p.tile) + tile_flat_words(p.st, p.tile)) * sizeof(uint32_t);
     const unsigned egrid = (unsigned)((n + p.tile - 1) / p.tile);
     if (obs->format == SPARC_OBS_COMPACT) k_encode<SPARC_OBS_COMPACT><<<egrid, ENC_THREADS, shmem, (cudaStream_t)stream>>>(p, 0, n);
@@ -875,6 +646,7 @@ int sparc_encode(SparcEnv* e, const SparcObsOut* obs, void* stream) {
 int sparc_validate(SparcEnv* e, const uint8_t* mask_dev, uint16_t* flags_dev, int8_t* region_map_dev,
                    int8_t* region_fit_dev, void* stream) {
     if (!e) return fail(SPARC_E_ARG, "null env%s");
+    CU(cudaSetDevice(e->store->device));
     const int64_t n = e->cfg.n_envs;
     k_validate<<<(unsigned)((n + CTA_THREADS - 1) / CTA_THREADS), CTA_THREADS, 0, (cudaStream_t)stream>>>(
         e->store->d, e->s, n, mask_dev, flags_dev, region_map_dev, region_fit_dev);
@@ -885,6 +657,7 @@ int sparc_validate(SparcEnv* e, const uint8_t* mask_dev, uint16_t* flags_dev, in
 
 int sparc_stats(SparcEnv* e, int64_t* out_dev, int clear, void* stream) {
     if (!e || !out_dev) return fail(SPARC_E_ARG, "null argument%s");
+    CU(cudaSetDevice(e->store->device));
     k_read_stats<<<1, 32 * SPARC_N_STATS, 0, (cudaStream_t)stream>>>(e->s.stats, (long long*)out_dev, clear);
     CU(cudaGetLastError());
     e->launches++;
@@ -921,6 +694,7 @@ int64_t sparc_state_bytes(const SparcEnv* e) {
 }
 
 static int state_copy(SparcEnv* e, char* blob, bool save, void* stream) {
+    CU(cudaSetDevice(e->store->device));
     const size_t n = (size_t)e->cfg.n_envs;
     struct { void* p; size_t bytes; } parts[] = {{e->s.core, n * 16}, {e->s.vis, n * 32}, {e->s.ep_ret, n * 4},
                                                  {e->s.moves, e->s.moves ? n * SPARC_MOVE_WORDS * 4 : 0}};
@@ -938,14 +712,6 @@ int sparc_state_save(SparcEnv* e, void* blob_dev, void* stream) {
 int sparc_state_load(SparcEnv* e, const void* blob_dev, void* stream) {
     if (!e || !blob_dev) return fail(SPARC_E_ARG, "null argument%s");
     return state_copy(e, (char*)blob_dev, false, stream);
-}
-
-int sparc_debug_counters(SparcEnv* e, uint64_t* out5_host) {   /* RING_PROFILE builds only: producer wait / dynamics / build, consumer wait / expand cycles */
-    if (!e || !out5_host) return fail(SPARC_E_ARG, "null argument%s");
-    CU(cudaDeviceSynchronize());
-    CU(cudaMemcpy(out5_host, e->sched + 2, 5 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
-    CU(cudaMemset(e->sched + 2, 0, 5 * sizeof(uint64_t)));
-    return SPARC_OK;
 }
 
 int sparc_debug_valprof(uint64_t* out8_host, int clear) {     /* -DVAL_PROFILE builds only: see VP_* in sparc_core.cuh, tools/valprof.py */

@@ -114,6 +114,7 @@ struct StoreDev {
     const int32_t* info;           // [n][S]
     const SparcShape* shapes;
     const uint32_t* trie;          // [nodes][8]
+    const uint32_t* vrec;          // [n][8][24] validator records of the warp-cooperative k_val (sparc_val_warp.cuh); device builds only
 };
 
 // per-env state, struct of arrays over envs (coalesced: consecutive lanes = consecutive envs)
@@ -460,99 +461,146 @@ SPARC_HD uint64_t cnt4_eq(const Cnt4& c, int k) {
 // with instances left so that only those are visited, and a candidate placement costs ONE 16-byte load
 // (beside the encoder every load waits behind its store stream: the search went at ~0.75 us per node when
 // each candidate read five shape fields and two counter bytes from memory).
-SPARC_HD bool exact_fit(uint64_t region, int w, int h, const SparcShape* shapes, int ns,
-                        const Cnt8& n_poly, const Cnt8& n_ylop) {
+//
+// The search is written as init + one-node step so that a warp can run 32 copies of it on disjoint parts of
+// the tree (k_val: exact_fit_warp in sparc_val_warp.cuh): the first `nsplit` BRANCHING nodes on the way down (nodes
+// with two or more valid children) hand their children out by ordinal parity -- bit b of `code` at the b-th
+// branching node -- so the 2^nsplit codes partition the leaves and their OR is the answer.  nsplit = 0 is the
+// plain depth-first search.
+struct FitState {
+    Cnt4 c;                                                   // net demand per cell
+    Cnt8 rem_p, rem_y;                                        // instances left per slot
+    uint64_t grid;
+    uint32_t have_p, have_y, mono_slots;
+    int tot_p, tot_y, level, cell, q;
+    int b;                                                    // branching nodes above the current node (capped use: b < nsplit)
+    int ord;                                                  // ordinal of the next valid child of the current node
+    bool all_connected, resumed, split;
+    uint8_t fr_cell[128], fr_q[128], fr_ord[128];             // DFS edges: q < 2ns placement, 0xFF = advance; ordinal | split << 7
+};
+
+// -1 = search on, 0 = no fit, 1 = fits
+SPARC_HD int fit_init(FitState& f, uint64_t region, int w, int h, const SparcShape* shapes, int ns,
+                      const Cnt8& n_poly, const Cnt8& n_ylop) {
     SPARC_COUNT_FIT_CALL();
-    Cnt8 rem_p = n_poly, rem_y = n_ylop;
-    uint8_t fr_cell[128], fr_q[128];                          // DFS edges: q < 2ns placement, 0xFF = advance
-    int tot_p = 0, tot_y = 0;
-    uint32_t have_p = 0, have_y = 0, mono_slots = 0;
-    bool all_connected = true;
+    f.rem_p = n_poly; f.rem_y = n_ylop;
+    f.tot_p = 0; f.tot_y = 0; f.have_p = 0; f.have_y = 0; f.mono_slots = 0; f.all_connected = true;
     // isolated-cell prune: once no ylop is left, a demanded cell with no demanded 4-neighbour can only be
     // covered by a one-cell poly (every other shape is 4-connected and would need a neighbour)
     for (int s = 0; s < ns; s++) {
         const ShapeW sh = load_shape(shapes + s);
         const int fl = shp_flags(sh.mask);
-        int np = cnt8_get(rem_p, s), ny = cnt8_get(rem_y, s);
-        if (fl & 2) { cnt8_add(rem_p, s, -np); cnt8_add(rem_y, s, -ny); np = ny = 0; }   // zero-area shapes never touch the grid
-        if ((np | ny) && !(sh.anchors & SPARC_CELLS56)) return false;       // fits nowhere on this board
-        tot_p += np; tot_y += ny;
-        if (np) { have_p |= 1u << s; if (!(fl & 4)) all_connected = false; }
-        if (ny) have_y |= 1u << s;
-        if ((sh.mask & SPARC_CELLS56) == 1ull) mono_slots |= 1u << s;
+        int np = cnt8_get(f.rem_p, s), ny = cnt8_get(f.rem_y, s);
+        if (fl & 2) { cnt8_add(f.rem_p, s, -np); cnt8_add(f.rem_y, s, -ny); np = ny = 0; }   // zero-area shapes never touch the grid
+        if ((np | ny) && !(sh.anchors & SPARC_CELLS56)) return 0;          // fits nowhere on this board
+        f.tot_p += np; f.tot_y += ny;
+        if (np) { f.have_p |= 1u << s; if (!(fl & 4)) f.all_connected = false; }
+        if (ny) f.have_y |= 1u << s;
+        if ((sh.mask & SPARC_CELLS56) == 1ull) f.mono_slots |= 1u << s;
     }
-    if (tot_y > SPARC_MAX_YLOPS) return false;                // (ingest guarantees this never happens)
-    Cnt4 c = {region, 0, 0, 0};
-    uint64_t grid = 0;
-    for (int cx = 0; cx < w; cx++) grid |= ((1ull << h) - 1ull) << (cx * 8);
-    int level = 0, cell = 0, q = 0;
-    if (tot_y == 0) cell = sp_ffsll(region) - 1;              // no ylops: only demanded cells ever matter
-    for (;;) {
-        SPARC_COUNT_FIT();
-        const int n = cnt4_get(c, cell);
-        const uint64_t later = grid & ~((2ull << cell) - 1ull);               // cells after `cell`
-        const uint64_t floor_cells = cnt4_eq(c, -tot_y) & later;              // later cells already at what ylops can lift
-        bool found = false;
-        if (q < ns && n + 1 <= tot_p) {                                       // anchor a ylop here (slots >= q)
-            for (uint32_t cand = have_y & (0xFFFFFFFFu << q); cand; cand &= cand - 1) {
-                const int s = sp_ffs(cand) - 1;
-                const uint64_t m = shape_at(load_shape(shapes + s), cell);
-                if (!m) continue;
-                if (floor_cells & ~m) continue;               // one ylop fewer can lift later cells: those at the floor would be lost
-                cnt4_add(c, m); cnt8_add(rem_y, s, -1); tot_y--;
-                if (!cnt8_get(rem_y, s)) have_y &= ~(1u << s);
-                fr_cell[level] = (uint8_t)cell; fr_q[level] = (uint8_t)s; level++;
-                q = s; found = true;
-                break;
-            }
-        }
-        if (!found && n > 0) {                                                // anchor a poly here (slots >= q - ns)
-            const int q2 = q > ns ? q - ns : 0;
-            for (uint32_t cand = q2 < 32 ? have_p & (0xFFFFFFFFu << q2) : 0u; cand; cand &= cand - 1) {
-                const int s = sp_ffs(cand) - 1;
-                const uint64_t m = shape_at(load_shape(shapes + s), cell);
-                if (!m) continue;
-                if (floor_cells & m) continue;                // would sink below what ylops can lift
-                cnt4_sub(c, m); cnt8_add(rem_p, s, -1); tot_p--;
-                if (tot_y == 0 && all_connected) {
-                    const uint64_t D = (c.b0 | c.b1 | c.b2) & ~c.b3;          // cells still demanded
-                    const uint64_t iso = D & ~((D << 1) | (D >> 1) | (D << 8) | (D >> 8));
-                    if (iso) {
-                        int monos = 0;
-                        for (uint32_t ms = mono_slots; ms; ms &= ms - 1) monos += cnt8_get(rem_p, sp_ffs(ms) - 1);
-                        if (sp_popcll(iso) > monos) { cnt4_add(c, m); cnt8_add(rem_p, s, 1); tot_p++; continue; }
-                    }
-                }
-                if (!cnt8_get(rem_p, s)) have_p &= ~(1u << s);
-                fr_cell[level] = (uint8_t)cell; fr_q[level] = (uint8_t)(ns + s); level++;
-                q = ns + s; found = true;
-                break;
-            }
-        }
-        if (found) continue;
-        if (n == 0) {                                                         // settled: advance
-            const uint64_t open = (c.b0 | c.b1 | c.b2 | c.b3) & later;        // later cells with non-zero demand
-            if (tot_p + tot_y == 0) { if (!open) return true; }               // nothing left and nothing demanded
-            else if (later && (tot_y > 0 || open)) {
-                // with ylops still to place every later cell is a candidate anchor; without, only a
-                // demanded cell can take a poly, so jump straight to the next one
-                fr_cell[level] = (uint8_t)cell; fr_q[level] = 0xFF; level++;
-                cell = sp_ffsll(tot_y > 0 ? later : open) - 1; q = 0;
-                continue;
-            }
-        }
-        for (;;) {                                                            // backtrack
-            if (level == 0) return false;
-            level--;
-            cell = fr_cell[level];
-            const int qq = fr_q[level];
-            if (qq == 0xFF) continue;                                         // advance was the last child
-            if (qq < ns) { cnt4_sub(c, shape_at(load_shape(shapes + qq), cell)); cnt8_add(rem_y, qq, 1); tot_y++; have_y |= 1u << qq; }
-            else { cnt4_add(c, shape_at(load_shape(shapes + qq - ns), cell)); cnt8_add(rem_p, qq - ns, 1); tot_p++; have_p |= 1u << (qq - ns); }
-            q = qq + 1;
-            break;
+    if (f.tot_y > SPARC_MAX_YLOPS) return 0;                  // (ingest guarantees this never happens)
+    f.c.b0 = region; f.c.b1 = 0; f.c.b2 = 0; f.c.b3 = 0;
+    f.grid = 0;
+    for (int cx = 0; cx < w; cx++) f.grid |= ((1ull << h) - 1ull) << (cx * 8);
+    f.level = 0; f.cell = 0; f.q = 0; f.b = 0; f.ord = 0; f.resumed = false; f.split = false;
+    if (f.tot_y == 0) f.cell = sp_ffsll(region) - 1;          // no ylops: only demanded cells ever matter
+    return -1;
+}
+
+// candidate children of the current node: a ylop / a poly of slot s anchored at f.cell
+SPARC_HD bool fit_ylop_ok(const FitState& f, const SparcShape* shapes, int s, uint64_t floor_cells, uint64_t& m) {
+    m = shape_at(load_shape(shapes + s), f.cell);
+    return m && !(floor_cells & ~m);                          // one ylop fewer can lift later cells: those at the floor would be lost
+}
+SPARC_HD bool fit_poly_ok(const FitState& f, const SparcShape* shapes, int s, uint64_t floor_cells, uint64_t& m) {
+    m = shape_at(load_shape(shapes + s), f.cell);
+    if (!m || (floor_cells & m)) return false;                // would sink below what ylops can lift
+    if (f.tot_y == 0 && f.all_connected) {
+        Cnt4 c = f.c;
+        cnt4_sub(c, m);
+        const uint64_t D = (c.b0 | c.b1 | c.b2) & ~c.b3;      // cells still demanded
+        const uint64_t iso = D & ~((D << 1) | (D >> 1) | (D << 8) | (D >> 8));
+        if (iso) {
+            int monos = -(int)((f.mono_slots >> s) & 1u);
+            for (uint32_t ms = f.mono_slots; ms; ms &= ms - 1) monos += cnt8_get(f.rem_p, sp_ffs(ms) - 1);
+            if (sp_popcll(iso) > monos) return false;
         }
     }
+    return true;
+}
+
+SPARC_HD int fit_step(FitState& f, const SparcShape* shapes, int ns, int code, int nsplit) {
+    SPARC_COUNT_FIT();
+    const int n = cnt4_get(f.c, f.cell);
+    const uint64_t later = f.grid & ~((2ull << f.cell) - 1ull);                 // cells after `cell`
+    const uint64_t floor_cells = cnt4_eq(f.c, -f.tot_y) & later;                // later cells already at what ylops can lift
+    const uint64_t open = (f.c.b0 | f.c.b1 | f.c.b2 | f.c.b3) & later;          // later cells with non-zero demand
+    const uint32_t ycand = (f.q < ns && n + 1 <= f.tot_p) ? f.have_y & (0xFFFFFFFFu << f.q) : 0u;   // ylops here (slots >= q)
+    const int q2 = f.q > ns ? f.q - ns : 0;
+    const uint32_t pcand = (n > 0 && q2 < 32) ? f.have_p & (0xFFFFFFFFu << q2) : 0u;               // polys here (slots >= q - ns)
+    // settled cell with work left: with ylops still to place every later cell is a candidate anchor; without, only
+    // a demanded cell can take a poly, so the advance jumps straight to the next one
+    const bool adv = n == 0 && (f.tot_p + f.tot_y) != 0 && later && (f.tot_y > 0 || open);
+    uint64_t m;
+    if (!f.resumed) {                                                           // first arrival at this node
+        f.ord = 0; f.split = false;
+        if (f.b < nsplit) {
+            int kids = adv ? 1 : 0;
+            for (uint32_t cand = ycand; cand; cand &= cand - 1) kids += fit_ylop_ok(f, shapes, sp_ffs(cand) - 1, floor_cells, m) ? 1 : 0;
+            for (uint32_t cand = pcand; cand; cand &= cand - 1) kids += fit_poly_ok(f, shapes, sp_ffs(cand) - 1, floor_cells, m) ? 1 : 0;
+            f.split = kids >= 2;
+        }
+    }
+    f.resumed = false;
+    const int skip = f.split ? ((code >> f.b) & 1) : 0;                         // this copy takes ordinals of the other parity
+    const uint8_t tag = (uint8_t)(f.split ? 0x80 : 0);
+    for (uint32_t cand = ycand; cand; cand &= cand - 1) {                       // anchor a ylop here
+        const int s = sp_ffs(cand) - 1;
+        if (!fit_ylop_ok(f, shapes, s, floor_cells, m)) continue;
+        if (f.split && ((f.ord ^ skip) & 1)) { f.ord++; continue; }
+        cnt4_add(f.c, m); cnt8_add(f.rem_y, s, -1); f.tot_y--;
+        if (!cnt8_get(f.rem_y, s)) f.have_y &= ~(1u << s);
+        f.fr_cell[f.level] = (uint8_t)f.cell; f.fr_q[f.level] = (uint8_t)s; f.fr_ord[f.level] = (uint8_t)(f.ord | tag); f.level++;
+        f.q = s; f.b += f.split ? 1 : 0;
+        return -1;
+    }
+    for (uint32_t cand = pcand; cand; cand &= cand - 1) {                       // anchor a poly here
+        const int s = sp_ffs(cand) - 1;
+        if (!fit_poly_ok(f, shapes, s, floor_cells, m)) continue;
+        if (f.split && ((f.ord ^ skip) & 1)) { f.ord++; continue; }
+        cnt4_sub(f.c, m); cnt8_add(f.rem_p, s, -1); f.tot_p--;
+        if (!cnt8_get(f.rem_p, s)) f.have_p &= ~(1u << s);
+        f.fr_cell[f.level] = (uint8_t)f.cell; f.fr_q[f.level] = (uint8_t)(ns + s); f.fr_ord[f.level] = (uint8_t)(f.ord | tag); f.level++;
+        f.q = ns + s; f.b += f.split ? 1 : 0;
+        return -1;
+    }
+    if (n == 0 && f.tot_p + f.tot_y == 0 && !open) return 1;                    // nothing left and nothing demanded
+    if (adv && !(f.split && ((f.ord ^ skip) & 1))) {
+        f.fr_cell[f.level] = (uint8_t)f.cell; f.fr_q[f.level] = 0xFF; f.fr_ord[f.level] = (uint8_t)(f.ord | tag); f.level++;
+        f.cell = sp_ffsll(f.tot_y > 0 ? later : open) - 1; f.q = 0; f.b += f.split ? 1 : 0;
+        return -1;
+    }
+    for (;;) {                                                                  // backtrack
+        if (f.level == 0) return 0;
+        f.level--;
+        f.cell = f.fr_cell[f.level];
+        const int qq = f.fr_q[f.level], o = f.fr_ord[f.level];
+        f.b -= o >> 7;
+        if (qq == 0xFF) continue;                                               // advance was the last child
+        if (qq < ns) { cnt4_sub(f.c, shape_at(load_shape(shapes + qq), f.cell)); cnt8_add(f.rem_y, qq, 1); f.tot_y++; f.have_y |= 1u << qq; }
+        else { cnt4_add(f.c, shape_at(load_shape(shapes + qq - ns), f.cell)); cnt8_add(f.rem_p, qq - ns, 1); f.tot_p++; f.have_p |= 1u << (qq - ns); }
+        f.q = qq + 1; f.ord = (o & 0x7f) + 1; f.split = (o >> 7) != 0; f.resumed = true;
+        return -1;
+    }
+}
+
+// one copy of the search: `code` / `nsplit` select its share of the tree (0, 0 = all of it)
+SPARC_HD bool exact_fit(uint64_t region, int w, int h, const SparcShape* shapes, int ns,
+                        const Cnt8& n_poly, const Cnt8& n_ylop, int code = 0, int nsplit = 0) {
+    FitState f;
+    int r = fit_init(f, region, w, h, shapes, ns, n_poly, n_ylop);
+    while (r < 0) r = fit_step(f, shapes, ns, code, nsplit);
+    return r != 0;
 }
 
 // vd: the env's visited plane in dense slab order, 9 readable words (word 8 may be anything
@@ -1107,8 +1155,10 @@ SPARC_HD bool phase_a(const KParams& p, long long i, EnvRegs& e, uint32_t* scrat
     if (p.mode == 1) {                                                   // ---- reset (SG.py:1057-1108)
         const bool sel = p.reset_mask ? p.reset_mask[i] != 0 : true;
         if (sel) {
-            uint32_t pz = p.reset_idx ? (uint32_t)p.reset_idx[i] : e.puzzle;
-            if (pz >= (uint32_t)st.n_puzzles) pz %= (uint32_t)st.n_puzzles;
+            // indices are taken modulo the pool, Python style (-1 = the last puzzle); host wrappers range-check first
+            int pzi = p.reset_idx ? p.reset_idx[i] % st.n_puzzles : (int)e.puzzle;
+            if (pzi < 0) pzi += st.n_puzzles;
+            const uint32_t pz = (uint32_t)pzi;
             env_reset(e, st, pz);
             store_env(e, p.sd, st, n, i);
             new_episode = true;
@@ -1209,9 +1259,6 @@ SPARC_HD int validate_queued(const KParams& p, uint32_t slot) {
 #pragma unroll
     for (int k = 0; k < 8; k++) vd[k] = q[4 + k];
     vd[8] = 0;
-#ifdef VAL_SKIP_HEAVY      /* timing experiment only: pretend long paths need no validation */
-    { int pc = 0; for (int k = 0; k < 8; k++) pc += sp_popc(vd[k]); if (pc > VAL_SKIP_HEAVY) return 0; }
-#endif
     const int f = validate_env(p.st, q[1], vd, (int)(q[2] & 0xff), (int)((q[2] >> 8) & 0xff), nullptr) | SPARC_RULE_VALID;
     if (p.out.rule_flags_dev) p.out.rule_flags_dev[q[0]] = (uint16_t)f;
     return (f & SPARC_RULE_ALL) != 0;

@@ -21,7 +21,7 @@ static StoreDev make_store(const SparcStoreDesc* d) {
     s.inv_wsc = (uint32_t)((1ull << 32) / (uint64_t)(s.Wc + 2)) + 1u;
     s.inv_wsz = (uint32_t)((1ull << 32) / (uint64_t)(s.nv + 2)) + 1u;
     s.hdr = d->headers; s.nb = d->node_boards; s.cb = d->cell_boards; s.sbits = d->static_bits;
-    s.color4 = d->color4; s.info_nz = d->info_nz; s.info = d->info; s.shapes = d->shapes; s.trie = d->trie;
+    s.color4 = d->color4; s.info_nz = d->info_nz; s.info = d->info; s.shapes = d->shapes; s.trie = d->trie; s.vrec = nullptr;
     return s;
 }
 
@@ -131,6 +131,16 @@ int emu_exact_fit(int which, uint64_t region, int w, int h, const SparcShape* sh
     for (int s = 0; s < ns; s++) { cnt8_add(np, s, n_poly[s]); cnt8_add(ny, s, n_ylop[s]); }
     const bool ok = which ? exact_fit_reference_order(region, w, h, shapes, ns, n_poly, n_ylop)
                           : exact_fit(region, w, h, shapes, ns, np, ny);
+    if (iters) *iters = g_fit_iters;
+    return ok ? 1 : 0;
+}
+// one copy of the split search (k_val runs the 2^nsplit codes on the lanes of a warp and ORs the answers)
+int emu_exact_fit_split(uint64_t region, int w, int h, const SparcShape* shapes, int ns, const uint8_t* n_poly,
+                        const uint8_t* n_ylop, int code, int nsplit, long long* iters) {
+    g_fit_iters = 0;
+    Cnt8 np = {{0, 0, 0, 0}}, ny = {{0, 0, 0, 0}};
+    for (int s = 0; s < ns; s++) { cnt8_add(np, s, n_poly[s]); cnt8_add(ny, s, n_ylop[s]); }
+    const bool ok = exact_fit(region, w, h, shapes, ns, np, ny, code, nsplit);
     if (iters) *iters = g_fit_iters;
     return ok ? 1 : 0;
 }

@@ -20,8 +20,13 @@ LIB.emu_exact_fit.argtypes = [C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_void_p,
                               C.POINTER(C.c_longlong)]
 
 
-def device_fit(which, X, Y, region, polys, ylops):
-    """polys / ylops: lists of shape arrays.  Returns (bool, search iterations)."""
+LIB.emu_exact_fit_split.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                    C.POINTER(C.c_longlong)]
+
+
+def device_fit(which, X, Y, region, polys, ylops, split=None):
+    """polys / ylops: lists of shape arrays.  Returns (bool, search iterations); with split=(code, nsplit) the answer
+    and effort of that one copy of the split search."""
     names = {}
     for a in polys + ylops:
         names.setdefault(json.dumps(a), len(names))
@@ -38,6 +43,10 @@ def device_fit(which, X, Y, region, polys, ylops):
     for (x, y) in region:
         reg |= 1 << ((x // 2) * 8 + (y // 2))
     it = C.c_longlong()
+    if split is not None:
+        ok = LIB.emu_exact_fit_split(C.c_uint64(reg), (X - 1) // 2, (Y - 1) // 2, slots.ctypes.data, len(names),
+                                     npoly.ctypes.data, nylop.ctypes.data, split[0], split[1], C.byref(it))
+        return bool(ok), it.value
     ok = LIB.emu_exact_fit(which, C.c_uint64(reg), (X - 1) // 2, (Y - 1) // 2, slots.ctypes.data, len(names),
                            npoly.ctypes.data, nylop.ctypes.data, C.byref(it))
     return bool(ok), it.value
@@ -169,3 +178,58 @@ def test_dense_boards_sweep_equals_reference_order():
             n += 1
             n_fit += a
     assert n > 20 and 0 < n_fit and worst < 200000, (n, n_fit, worst)
+
+
+def split_fit(X, Y, region, polys, ylops, nsplit=5):
+    """The 2^nsplit copies of the split search as k_val's lanes run them: (OR of the answers, node counts per copy).
+    A real warp stops all copies as soon as one finds a fit; here every copy runs to its own end."""
+    res = [device_fit(0, X, Y, region, polys, ylops, split=(code, nsplit)) for code in range(1 << nsplit)]
+    return any(r[0] for r in res), [r[1] for r in res]
+
+
+def test_split_search_partitions_the_tree():
+    """exact_fit(code, nsplit): the copies' answers OR to the plain search's answer (random cases with ylops, perturbed
+    unsolvable cases), and on unsolvable cases -- where every copy must exhaust its share -- no copy visits more nodes
+    than the plain search does, and together they visit it about once (shared trunk above the splits aside)."""
+    rng = np.random.default_rng(5)
+    n = n_fit = 0
+    while n < 400:
+        X, Y, region, polys, ylops = random_case(rng)
+        if not region or not polys or sum(map(area, polys)) - sum(map(area, ylops)) != len(region):
+            continue
+        want, it_plain = device_fit(0, X, Y, region, polys, ylops)
+        got, its = split_fit(X, Y, region, polys, ylops)
+        assert got == want, (X, Y, region, polys, ylops)
+        if not want:
+            assert max(its) <= it_plain, (its, it_plain)
+        n += 1
+        n_fit += want
+    assert n_fit > 80 and n - n_fit > 40
+
+
+def test_split_search_on_dense_boards():
+    """Dense 6x6 boards (the hard tail of DESIGN.md): answers agree and the slowest copy of an unsolvable or hard board
+    does a small fraction of the plain search's work."""
+    from sparc_gym_b200.dataset import SMALL_PIECES
+    rng = np.random.default_rng(1)
+    region = [(2 * i + 1, 2 * j + 1) for i in range(6) for j in range(6)]
+    ratios = []
+    for _ in range(25):
+        polys, tot = [], 0
+        while tot < 36:
+            q = SMALL_PIECES[int(rng.integers(len(SMALL_PIECES)))]
+            if tot + area(q) <= 36:
+                polys.append(q)
+                tot += area(q)
+            elif 36 - tot == 1:
+                break
+        if tot != 36:
+            continue
+        want, it_plain = device_fit(0, 13, 13, region, polys, [])
+        res = [device_fit(0, 13, 13, region, polys, [], split=(code, 5)) for code in range(32)]
+        assert any(r[0] for r in res) == want, polys
+        if it_plain > 2000:
+            # a warp ends when the first copy finds a fit (solvable) or when the slowest copy gives up (unsolvable)
+            warp_nodes = min(r[1] for r in res if r[0]) if want else max(r[1] for r in res)
+            ratios.append(warp_nodes / it_plain)
+    assert ratios and float(np.median(ratios)) < 0.5, ratios

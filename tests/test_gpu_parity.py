@@ -64,15 +64,15 @@ def test_maximum_lattice_and_non_square_boards():
     assert np.array_equal(to_np(g.stats()), c.stats()) and c.stats()[0] > 500
 
 
-@pytest.fixture(params=[("0", "0", "8"), ("0", "1", "32"), ("0", "0", "128"), ("3", "0", "8"), ("4", "0", "32"), ("1", "0", "4")],
-                ids=lambda p: f"split{p[0]}-ring{p[1]}-tile{p[2]}")
+@pytest.fixture(params=[("0", "8"), ("0", "32"), ("0", "128"), ("0", "20"), ("3", "8"), ("4", "32"), ("1", "4"), ("1", "36"), ("1", "128")],
+                ids=lambda p: f"split{p[0]}-tile{p[1]}")
 def kernel_variant(request, monkeypatch):
-    """Every launch strategy: fused k_env at several CTA tilings, the persistent warp-specialised ring
-    kernel, and the k_dyn || k_encode chunk pipeline (side stream + events)."""
+    """Every launch strategy: fused k_env at several CTA tilings (incl. tiles that are not multiples of 16, which the
+    compact format must round up, and the largest tile, which needs > 48 KB of dynamic shared memory), and the
+    k_dyn -> k_val || k_encode split (side stream + events), single- and multi-chunk."""
     monkeypatch.setenv("SPARC_SPLIT", request.param[0])
-    monkeypatch.setenv("SPARC_RING", request.param[1])
-    monkeypatch.setenv("SPARC_TILE", request.param[2])
-    monkeypatch.setenv("SPARC_ENC_TILE", request.param[2])
+    monkeypatch.setenv("SPARC_TILE", request.param[1])
+    monkeypatch.setenv("SPARC_ENC_TILE", request.param[1])
     return request.param
 
 
@@ -220,11 +220,15 @@ def test_dense_polyomino_boards_on_the_gpu(monkeypatch):
     assert st[0] == N and st[1] == N and 0 < st[7] < N      # every env walked its listed solution; some boards tile
 
 
-@pytest.mark.parametrize("n_envs", [333, 9000])
-def test_compact_observation_format_on_the_gpu(n_envs):
+@pytest.mark.parametrize("n_envs,tile", [(333, None), (9000, None), (333, "20"), (9000, "36"), (9000, "128"), (333, "128")])
+def test_compact_observation_format_on_the_gpu(n_envs, tile, monkeypatch):
     """obs_format='compact' (uint8 / uint8 / int32) holds the same values as the reference-dtype observation,
     element for element, through the fused kernel (333 envs) and the split k_dyn / k_encode step (9,000 envs);
-    sparc_encode rewrites it from the state alike."""
+    sparc_encode rewrites it from the state alike.  Tile overrides that are not multiples of 16 are rounded up (16-byte
+    stores of uint8 streams), the largest tile needs more than 48 KB of dynamic shared memory."""
+    if tile:
+        monkeypatch.setenv("SPARC_TILE", tile)
+        monkeypatch.setenv("SPARC_ENC_TILE", tile)
     rows = gen_pool(12, [(3, 3), (4, 4), (5, 5), (6, 6)], RULES_FULL, seed0=60)
     kw = dict(traceback=True, max_steps=25, autoreset_mode="same_step", validate="terminal")
     a = make_env(rows, n_envs, **kw)

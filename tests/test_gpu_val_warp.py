@@ -1,0 +1,78 @@
+"""GPU: the warp-cooperative terminal validator (k_val -> validate_warp, sparc_val_warp.cuh) against the scalar
+validator (k_validate -> validate_env, the code the CPU build of the tests pins to the oracle) on the SAME terminal
+states, at split-step batch sizes: fuzzed rows (stacked / off-region ylops, colliding triangle counts, multi-instance
+shapes, colourless stars), generated full-rule boards of every size, and dense polyomino boards whose exact-fit
+search needs 1e3..1e4 nodes (the 32-way split search).  Envs freeze when they finish (autoreset disabled), so the
+state k_val judged is still there for sparc_validate to judge again."""
+import numpy as np
+import pytest
+import torch
+
+from fuzzrows import fuzz_row, solution_actions
+from sparc_gym_b200.dataset import RULES_FULL, gen_dense_poly_puzzle, gen_pool
+
+pytestmark = pytest.mark.gpu
+
+
+def _policy_table(rows, T, rng):
+    """Per puzzle an action row: its listed solution (when it has one), padded with random actions."""
+    table = rng.integers(0, 4, (len(rows), T)).astype(np.uint8)
+    for i, r in enumerate(rows):
+        if r["solutions"]:
+            s = solution_actions(r, int(rng.integers(len(r["solutions"]))))[:T]
+            table[i, :len(s)] = s
+    return table
+
+
+def _run(rows, N, T, traceback, max_steps, seed, follow):
+    from sparc_gym_b200.vec_env import SparcVecEnv
+    rng = np.random.default_rng(seed)
+    env = SparcVecEnv(rows, N, traceback=traceback, max_steps=max_steps, autoreset_mode="disabled", validate="terminal")
+    assert N >= 8192                                         # the split step: k_dyn -> k_val || k_encode
+    table = _policy_table(rows, T, rng)
+    pz = np.arange(N) % len(rows)
+    # an env follows its puzzle's row up to a random deviation step, then plays randomly
+    dev = np.where(rng.random(N) < follow, T, rng.integers(0, T, N))
+    env.reset()
+    judged = wins = passes = 0
+    for t in range(T):
+        a = np.where(t < dev, table[pz, t], rng.integers(0, 5, N)).astype(np.uint8)     # 4 = an invalid action id
+        _, _, te, tr, info = env.step(torch.from_numpy(a).cuda())
+        flags = info["rule_flags"].to(torch.int32) & 0xFFFF
+        fresh = (flags & 0x8000) != 0                        # validated this step = finished this step
+        done = (te | tr).bool()
+        assert bool((fresh <= done).all())
+        if not bool(fresh.any()):
+            continue
+        scalar = env.validate(mask=fresh).to(torch.int32) & 0xFFFF
+        bad = fresh & (scalar != flags)
+        if bool(bad.any()):
+            i = int(torch.nonzero(bad)[0])
+            raise AssertionError(f"step {t}, env {i}, puzzle {rows[pz[i]]['id']}: k_val {int(flags[i]):#06x} != k_validate "
+                                 f"{int(scalar[i]):#06x}; {int(bad.sum())} of {int(fresh.sum())} differ")
+        judged += int(fresh.sum())
+        wins += int((fresh & (info["reward_code"] == 3)).sum())
+        passes += int((fresh & ((flags & 0x100) != 0)).sum())
+    st = env.stats().cpu().tolist()
+    assert st[0] == judged and st[7] == passes               # RULES_PASS is counted by k_val
+    return judged, wins, passes
+
+
+def test_fuzzed_rows():
+    rows = [fuzz_row(s) for s in range(700, 820)]
+    judged, wins, passes = _run(rows, 8192 + 77, 48, True, 40, seed=1, follow=0.5)
+    assert judged > 6000 and passes > 50
+
+
+@pytest.mark.parametrize("traceback", [False, True])
+def test_generated_full_rule_boards(traceback):
+    rows = gen_pool(96, [(1, 1), (2, 3), (3, 3), (4, 4), (5, 5), (6, 6), (7, 7), (6, 3)], RULES_FULL, seed0=4000, extra_solutions=1)
+    judged, wins, passes = _run(rows, 16384, 150, traceback, 140, seed=2, follow=0.6)
+    assert judged > 12000 and wins > 5000 and passes > 5000
+
+
+def test_dense_polyomino_boards():
+    rows = [gen_dense_poly_puzzle(6, 6, s) for s in range(40)] + [gen_dense_poly_puzzle(5, 4, s) for s in range(8)] + \
+        gen_pool(16, [(6, 6)], RULES_FULL, seed0=9000)
+    judged, wins, passes = _run(rows, 8192, 30, False, 100, seed=3, follow=0.9)
+    assert judged > 5000 and wins > 5000 and 0 < passes < judged      # some dense boards tile, most do not
