@@ -36,6 +36,7 @@ static int fail(int code, const char* fmt, const char* detail = "") {
 
 struct SparcStore {
     int device;
+    int max_instances;       // most poly / ylop instances in one puzzle of the pool
     StoreDev d;
     void* blocks[10];
     int plane_ids[SPARC_MAX_PLANES];
@@ -55,10 +56,13 @@ struct SparcEnv {
     struct { float* reward; uint8_t* term; uint8_t* trunc; bool active; } hostcopy;
     uint32_t* vq_count;      // deferred-validation queue (split path, validate = terminal)
     uint32_t* vq;
+    uint32_t* hq_count;      // hard items (exact-fit searches over budget): items, shares handed out, finished CTAs
+    uint4* hq;               // [n_envs]
+    int hard_search;         // the pool can produce big exact-fit searches: node budgets + k_val_hard (see push_hard_item)
     uint32_t* rq_count;      // update = SPARC_OBS_DELTA: envs that began a new episode this step (count, finished CTAs)
     uint32_t* rq;            // [n_envs]
     int val_grid;            // CTAs of k_val beside the full-rewrite encoder
-    int val_grid_delta;      // ... when nothing but k_encode_list runs beside it (update = SPARC_OBS_DELTA)
+    int val_grid_delta;      // most CTAs of k_post (update = SPARC_OBS_DELTA)
     int64_t launches;
     uint8_t* act_stage;      // device staging for the *_host call
     float* rew_stage;
@@ -172,24 +176,91 @@ __global__ void __launch_bounds__(CTA_THREADS, DYN_MINBLOCKS) k_dyn(const KParam
 // sparc_val_warp.cuh: boards one word per lane, region rules one colour / one shape slot per lane, the exact-fit search
 // split over the lanes).  Round 1 ran one snapshot per thread: 10.7 us of lone dependent chain each, 7.6 of 32 lanes
 // active, the kernel as long as its slowest thread (24-39 us typical, 408 us at worst: profiles/r1_valprof.txt).
+// Hard items: a snapshot whose exact-fit search outgrows the validating kernel's node budget (dense polyomino boards:
+// 1e3..1e5 nodes; one node costs 0.1-0.8 us in one warp whatever its lanes do, so a big search needs many warps).
+// Budgets and k_val_hard exist only for pools that can produce such searches (SparcEnv::hard_search: some puzzle holds
+// eight or more shape instances, or SPARC_HARD_SEARCH=1): for other pools every search runs inline and k_val_hard is
+// not launched at all -- its idle launch costs 2-3 us of every step, and an item costs more than an inline search of
+// a few hundred nodes (measured, 131,072 envs of the config-4 pool, rewrite / compact step in ms: unlimited inline
+// search 0.1825 / 0.0806, budget 768 + k_val_hard 0.1863 / 0.0859, budget 256 0.1891 / 0.0881).  Also measured and
+// dropped: the items taken by lingering warps of the validating kernel itself (too few warps beside the encoder: p99
+// 10.9 ms on dense boards) and a device-side tail launch of k_val_hard (-rdc slowed every kernel: step 0.186 -> 0.211 ms).
+// hq_count words: 0 items, 1 shares handed out, 2 finished CTAs of k_val_hard.  hq item (uint4): queue slot, shares
+// finished, found mask (64 bits).
+__device__ __forceinline__ void push_hard_item(const KParams& p, uint32_t slot) {
+    p.hq[atomicAdd(p.hq_count, 1u)] = make_uint4(slot, 0u, 0u, 0u);
+}
+
+// Terminal validation BESIDE the full-rewrite encoder: one snapshot per thread, a small grid.  k_encode fills the
+// register file (9 CTAs x 56 registers x 128 threads per SM), so every validator CTA displaces encoder CTAs for as
+// long as it runs; what counts here is snapshots per resident warp, not latency, and 32 diverging lanes that each
+// carry a snapshot get through ~2.5x more of them per warp-second than a converged warp that takes them one by one
+// (measured at 131,072 envs, ~2,230 snapshots per step, 32 CTAs: this kernel 20-50 us alone, the warp-per-snapshot
+// one ~75 us alone and longer than the encoder beside it).
+// Snapshots are dealt out warp by warp (slot s -> warp s mod nwarps): the fewer diverging lanes share a warp, the shorter.
 __global__ void __launch_bounds__(CTA_THREADS) k_val(const KParams p) {
     const uint32_t count = *p.vq_count;
-    const int lane = threadIdx.x & 31;
-    const uint32_t nwarps = gridDim.x * (CTA_THREADS / 32);
     unsigned long long pass = 0;
-    for (uint32_t slot = blockIdx.x * (CTA_THREADS / 32) + (threadIdx.x >> 5); slot < count; slot += nwarps) {
-        const uint32_t qw = lane < SPARC_VQ_WORDS ? p.vq[(size_t)slot * SPARC_VQ_WORDS + lane] : 0u;   // 48 contiguous bytes
-        const int f = validate_warp(p.st, qw, lane) | SPARC_RULE_VALID;
-        if (lane == 0) {
-            if (p.out.rule_flags_dev) p.out.rule_flags_dev[qw] = (uint16_t)f;                          // word 0 = env
-            pass += (f & SPARC_RULE_ALL) != 0;
-        }
+    const uint32_t nwarps = gridDim.x * (CTA_THREADS / 32);
+    const uint32_t warp = blockIdx.x * (CTA_THREADS / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    for (uint32_t slot = lane * nwarps + warp; slot < count; slot += 32 * nwarps) {
+        const int r = validate_queued(p, slot, p.fit_budget);
+        if (r < 0) push_hard_item(p, slot);
+        else pass += (unsigned long long)r;
     }
-    if (lane == 0 && pass) atomicAdd(p.sd.stats + SPARC_STAT_RULES_PASS, pass);
+#pragma unroll
+    for (int off = 16; off; off >>= 1) pass += __shfl_down_sync(0xffffffffu, pass, off);
+    if ((threadIdx.x & 31) == 0 && pass) atomicAdd(p.sd.stats + SPARC_STAT_RULES_PASS, pass);
     __syncthreads();                                             // every thread of the CTA has read `count`
     if (threadIdx.x == 0) {                                      // last CTA out empties the queue for the next step
         __threadfence();
         if (atomicAdd(p.vq_count + 1, 1u) == gridDim.x - 1) { p.vq_count[0] = 0; p.vq_count[1] = 0; }
+    }
+}
+
+// Each hard item is validated again by VW_HARD_CODES shares, share c searching part c of every search tree
+// (validate_warp<true> -> fit_step with code = c, the whole warp converged).  Shares are handed out through one
+// counter, so the 64 shares of a snapshot run wherever a warp is free.  A share that finds a fit sets the region's bit
+// in the item's found mask (and thereby stops its siblings); the last share of a snapshot to finish writes its flags.
+// One warp per CTA: beside k_encode a 128-thread CTA of this kernel would need the registers of three retiring encoder CTAs.
+#define HARD_CTAS 1184
+__global__ void __launch_bounds__(32) k_val_hard(const KParams p) {
+    const uint32_t n_items = p.hq_count[0];
+    const int lane = threadIdx.x & 31;
+    unsigned long long pass = 0;
+    if (!n_items) return;
+    const uint32_t total = n_items * VW_HARD_CODES;
+    for (;;) {
+        uint32_t w = 0;
+        if (lane == 0) w = atomicAdd(p.hq_count + 1, 1u);
+        w = __shfl_sync(0xffffffffu, w, 0);
+        if (w >= total) break;
+        uint4* item = p.hq + (w % n_items);                      // share-major: the snapshots start side by side
+        const int code = (int)(w / n_items);
+        const uint32_t slot = item->x;
+        const uint32_t qw = lane < SPARC_VQ_WORDS ? p.vq[(size_t)slot * SPARC_VQ_WORDS + lane] : 0u;
+        unsigned long long* found = reinterpret_cast<unsigned long long*>(&item->z);
+        unsigned long long fit_mask = 0;
+        int n_search = 0;
+        int f = validate_warp<true>(p.st, qw, lane, nullptr, 0, code, found, &fit_mask, &n_search);
+        if (lane == 0) {
+            if (fit_mask) atomicOr(found, fit_mask);
+            __threadfence();
+            if (atomicAdd(&item->y, 1u) == VW_HARD_CODES - 1) {                                       // last share of this snapshot
+                __threadfence();
+                const unsigned long long all = atomicOr(found, 0ull);
+                const unsigned long long need = n_search >= 64 ? ~0ull : (1ull << n_search) - 1ull;
+                if ((all & need) != need) f &= ~SPARC_RULE_POLY_YLOP;                                // some region has no tiling
+                if ((f & 0xFF) == 0xFF) f |= SPARC_RULE_ALL;
+                if (p.out.rule_flags_dev) p.out.rule_flags_dev[qw] = (uint16_t)(f | SPARC_RULE_VALID);       // word 0 = env
+                pass += (f & SPARC_RULE_ALL) != 0;
+            }
+        }
+    }
+    if (lane == 0) {
+        if (pass) atomicAdd(p.sd.stats + SPARC_STAT_RULES_PASS, pass);
+        __threadfence();                                         // last CTA out empties the hard queue
+        if (atomicAdd(p.hq_count + 2, 1u) == gridDim.x - 1) { p.hq_count[0] = 0; p.hq_count[1] = 0; p.hq_count[2] = 0; }
     }
 }
 
@@ -222,21 +293,41 @@ __global__ void __launch_bounds__(ENC_THREADS, ENC_MINBLOCKS) k_encode(const KPa
     encode_tile_stage2<FMT>(st, head, flats, p.tile, nE, env0, p.obs, tid, ENC_THREADS);
 }
 
-// update = SPARC_OBS_DELTA on the split path: k_dyn touches the changed cells in place and queues the envs that began a
-// new episode (1-2 % per step); this kernel rewrites those in full and leaves the queue empty.  One WARP per queue
-// entry (rows of tile = 1 in the warp's own slice of shared memory, __syncwarp between the stages): the first
-// version gave every entry a whole CTA and three block barriers and took 16.5 us for ~2,100 envs -- two waves of
-// mostly idle CTAs, each a chain of state load -> store loads -> stores.
+// update = SPARC_OBS_DELTA on the split path: k_dyn touches the changed cells in place, queues the envs that began a new
+// episode (1-2 % per step) and queues the terminal states; k_post does both follow-ups in ONE launch, one WARP per queue
+// entry: first the warp-cooperative rule validation of its snapshots (validate_warp, sparc_val_warp.cuh: ~4 us each,
+// the latency that bounds this step), then the full rewrite of its new-episode envs (rows of tile = 1 in the warp's own
+// slice of shared memory, element-wise stores).  As two kernels on two streams they did not overlap: a grid that gives
+// every snapshot its own warp fills the register file, so k_encode_list waited for k_val (step 0.046 ms = k_dyn 12 +
+// k_val 12 + k_encode_list 11 + launches); fused, every warp has work of both kinds.
+// Snapshots whose exact-fit search outgrows the node budget (pools with dense boards only) become hard items (k_val_hard).
 template <int FMT>
-__global__ void __launch_bounds__(ENC_THREADS) k_encode_list(const KParams p) {
+__global__ void __launch_bounds__(ENC_THREADS) k_post(const KParams p) {
+    __shared__ uint16_t fit_stack[ENC_THREADS / 32][128];
     const StoreDev& st = p.st;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const uint32_t count = *p.rq_count;
+    const uint32_t nwarps = gridDim.x * (ENC_THREADS / 32);
+    const uint32_t warp = blockIdx.x * (ENC_THREADS / 32) + wib;
+    unsigned long long pass = 0;
+    if (p.vq_count) {                                            // ---- terminal validation
+        const uint32_t count = *p.vq_count;
+        for (uint32_t slot = warp; slot < count; slot += nwarps) {
+            const uint32_t qw = lane < SPARC_VQ_WORDS ? p.vq[(size_t)slot * SPARC_VQ_WORDS + lane] : 0u;   // 48 contiguous bytes
+            const int f = validate_warp<false>(p.st, qw, lane, fit_stack[wib], p.fit_budget);
+            if (lane == 0) {
+                if (f < 0) push_hard_item(p, slot);
+                else {
+                    if (p.out.rule_flags_dev) p.out.rule_flags_dev[qw] = (uint16_t)(f | SPARC_RULE_VALID); // word 0 = env
+                    pass += (f & SPARC_RULE_ALL) != 0;
+                }
+            }
+        }
+    }
+    const uint32_t rcount = p.rq_count ? *p.rq_count : 0u;      // ---- envs that began a new episode: whole observation
     const int per_warp = tile_head_words(1) + tile_flat_words(st, 1);
     uint32_t* head = smem + wib * per_warp;
     uint32_t* flats = head + tile_head_words(1);
-    const uint32_t nwarps = gridDim.x * (ENC_THREADS / 32);
-    for (uint32_t slot = blockIdx.x * (ENC_THREADS / 32) + wib; slot < count; slot += nwarps) {
+    for (uint32_t slot = nwarps - 1 - warp; slot < rcount; slot += nwarps) {   // (the warps with one snapshot fewer go first)
         const long long env = (long long)p.rq[slot];
         if (lane == 0) {
             EnvRegs e;
@@ -250,10 +341,14 @@ __global__ void __launch_bounds__(ENC_THREADS) k_encode_list(const KParams p) {
         encode_env_elementwise<FMT>(st, head, flats, env, p.obs, lane, 32);
         __syncwarp();                                            // the rows are reused by the next pass
     }
-    __syncthreads();                                             // every thread of the CTA has read `count`
-    if (threadIdx.x == 0) {                                      // last CTA out empties the queue for the next step
+    if (lane == 0 && pass) atomicAdd(p.sd.stats + SPARC_STAT_RULES_PASS, pass);
+    __syncthreads();                                             // every thread of the CTA has read the counts
+    if (threadIdx.x == 0) {                                      // last CTA out empties both queues for the next step
         __threadfence();
-        if (atomicAdd(p.rq_count + 1, 1u) == gridDim.x - 1) { p.rq_count[0] = 0; p.rq_count[1] = 0; }
+        if (atomicAdd(p.rq_count + 1, 1u) == gridDim.x - 1) {
+            p.rq_count[0] = 0; p.rq_count[1] = 0;
+            if (p.vq_count) { p.vq_count[0] = 0; p.vq_count[1] = 0; }
+        }
     }
 }
 
@@ -357,6 +452,14 @@ int sparc_store_create(const SparcStoreDesc* desc, int device, SparcStore** out)
         sparc_store_destroy(s);
         return rc;
     }
+    for (size_t i = 0; i < n; i++) {
+        int inst = 0;
+        for (int k = 0; k < desc->headers[i].n_shapes; k++) {
+            const SparcShape& sh = desc->shapes[desc->headers[i].shape_off + k];
+            inst += __builtin_popcountll(sh.poly_cells) + __builtin_popcountll(sh.ylop_cells);
+        }
+        if (inst > s->max_instances) s->max_instances = inst;
+    }
     {   // validator records of k_val (layout: sparc_val_warp.cuh), assembled from the arrays above
         uint32_t* vr = new (std::nothrow) uint32_t[n * SPARC_VREC_WORDS];
         if (!vr) { sparc_store_destroy(s); return fail(SPARC_E_NOMEM, "out of host memory%s"); }
@@ -454,16 +557,18 @@ int sparc_env_create(SparcStore* store, int64_t n_envs, int traceback, int max_s
             if (se == cudaSuccess) se = cudaEventCreateWithFlags(&e->ev_copy, cudaEventDisableTiming);
             const char* de = getenv("SPARC_DEFER_VALIDATION");
             if (se == cudaSuccess && !(de && atoi(de) == 0)) {
-                se = cudaMalloc((void**)&e->vq_count, 2 * sizeof(uint32_t));   // count, finished k_val CTAs
+                se = cudaMalloc((void**)&e->vq_count, 4 * sizeof(uint32_t));   // see k_val
                 if (se == cudaSuccess) se = cudaMalloc((void**)&e->vq, (size_t)n_envs * SPARC_VQ_WORDS * sizeof(uint32_t));
-                if (se == cudaSuccess) se = cudaMemset(e->vq_count, 0, 2 * sizeof(uint32_t));
-                int dev_sms = 0;
-                cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, store->device);
-                (void)dev_sms;
-                e->val_grid = 148;             // x4 warps = snapshots in flight beside the full-rewrite encoder
+                if (se == cudaSuccess) se = cudaMemset(e->vq_count, 0, 4 * sizeof(uint32_t));
+                if (se == cudaSuccess) se = cudaMalloc((void**)&e->hq_count, 4 * sizeof(uint32_t));
+                if (se == cudaSuccess) se = cudaMalloc((void**)&e->hq, (size_t)n_envs * sizeof(uint4));
+                if (se == cudaSuccess) se = cudaMemset(e->hq_count, 0, 4 * sizeof(uint32_t));
+                const char* he = getenv("SPARC_HARD_SEARCH");                  // 0 / 1; unset = by the pool's densest puzzle
+                e->hard_search = he ? atoi(he) != 0 : store->max_instances >= 8;
+                e->val_grid = 32;              // x128 threads; a small grid disturbs the co-running encoder least (measured)
                 const char* ve = getenv("SPARC_VAL_GRID");
                 if (ve && atoi(ve) > 0) e->val_grid = atoi(ve);
-                e->val_grid_delta = 592;       // a warp per snapshot for ~2,400 snapshots (1.6 % of 131,072 envs end per step)
+                e->val_grid_delta = 592;       // k_post: at most one resident wave of warps, one queue entry each
                 const char* vd = getenv("SPARC_VAL_GRID_DELTA");
                 if (vd && atoi(vd) > 0) e->val_grid_delta = atoi(vd);
 
@@ -497,7 +602,7 @@ int sparc_env_create(SparcStore* store, int64_t n_envs, int traceback, int max_s
 int sparc_env_destroy(SparcEnv* e) {
     if (!e) return SPARC_OK;
     cudaSetDevice(e->store->device);
-    void* ptrs[] = {e->s.core, e->s.vis, e->s.ep_ret, e->s.moves, e->s.stats, e->vq_count, e->vq, e->rq_count, e->rq, e->act_stage, e->rew_stage, e->term_stage, e->trunc_stage};
+    void* ptrs[] = {e->s.core, e->s.vis, e->s.ep_ret, e->s.moves, e->s.stats, e->vq_count, e->vq, e->hq_count, e->hq, e->rq_count, e->rq, e->act_stage, e->rew_stage, e->term_stage, e->trunc_stage};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (e->side) cudaStreamDestroy(e->side);
     if (e->ev_start) cudaEventDestroy(e->ev_start);
@@ -533,9 +638,12 @@ static int launch_env(SparcEnv* e, KParams& p, void* stream) {
         cudaStream_t sd = nc > 1 ? e->side : s0;                         // one chunk: plain back-to-back launches
         const bool defer = p.mode == 0 && e->vq && e->cfg.validate_mode == SPARC_VALIDATE_TERMINAL;
         const bool delta = any_obs && p.obs.update == SPARC_OBS_DELTA;
-        if (delta) { p.rq = e->rq; p.rq_count = e->rq_count; }          // (k_encode_list leaves the queue empty)
+        if (delta) { p.rq = e->rq; p.rq_count = e->rq_count; }          // (k_post leaves the queue empty)
         if (defer) {
             p.vq = e->vq; p.vq_count = e->vq_count;                     // (k_val leaves the queue empty)
+            p.hq = e->hq; p.hq_count = e->hq_count;
+            // node budget of an inline exact-fit search (0 = none): one thread (k_val) / one converged warp (k_post)
+            p.fit_budget = e->hard_search ? (delta ? 128 : 192) : 0;
         }
         if (nc > 1) {
             CU(cudaEventRecord(e->ev_start, s0));
@@ -552,19 +660,20 @@ static int launch_env(SparcEnv* e, KParams& p, void* stream) {
                 CU(cudaStreamWaitEvent(s0, e->ev_dyn[c], 0));
             }
             const bool last = hi >= n;
-            const bool fork_val = defer && last;
+            const bool fork_val = defer && last && !delta;                   // (delta: k_post validates)
             const bool fork_copy = e->hostcopy.active && nc == 1;
             if (nc == 1 && (fork_val || fork_copy)) CU(cudaEventRecord(e->ev_start, s0));   // = k_dyn done
             if (delta) {
-                if (last) {                                                  // the envs that began a new episode, in full
+                if (last) {      // terminal validation + the envs that began a new episode in full: one warp per queue entry
                     const size_t shmem1 = (size_t)(ENC_THREADS / 32) * (tile_head_words(1) + tile_flat_words(p.st, 1)) * sizeof(uint32_t);
-                    // ~1.6 % of the envs end an episode per step under random play: one queue entry per warp pass when the
-                    // grid's warps cover n / 32 entries; at most one resident wave (warps beyond the queue leave at once)
-                    int64_t want = (n + 127) / 128;
-                    if (want > 148 * 8) want = 148 * 8;
-                    const unsigned lgrid = (unsigned)(want < 1 ? 1 : want);
-                    if (compact) k_encode_list<SPARC_OBS_COMPACT><<<lgrid, ENC_THREADS, shmem1, s0>>>(p);
-                    else k_encode_list<SPARC_OBS_REFERENCE><<<lgrid, ENC_THREADS, shmem1, s0>>>(p);
+                    // ~1.6 % of the envs end an episode per step under random play: a warp per entry when the grid's warps
+                    // cover n / 55 entries; at most one resident wave (4 CTAs per SM at k_post's registers)
+                    int64_t want = (n + 219) / 220;
+                    if (want > e->val_grid_delta) want = e->val_grid_delta;
+                    const unsigned pgrid = (unsigned)(want < 1 ? 1 : want);
+                    if (compact) k_post<SPARC_OBS_COMPACT><<<pgrid, ENC_THREADS, shmem1, s0>>>(p);
+                    else k_post<SPARC_OBS_REFERENCE><<<pgrid, ENC_THREADS, shmem1, s0>>>(p);
+                    if (defer && e->hard_search) { k_val_hard<<<HARD_CTAS, 32, 0, s0>>>(p); e->launches++; }
                 }
             } else if (any_obs) {
                 const unsigned egrid = (unsigned)((hi - lo + p.tile - 1) / p.tile);
@@ -583,8 +692,8 @@ static int launch_env(SparcEnv* e, KParams& p, void* stream) {
             // from a full register file -- changed nothing: compact 0.0833 vs 0.0833 ms, reference 0.1861 vs 0.1850.)
             if (fork_val) {                                                  // k_val beside (the last) k_encode
                 if (nc == 1) CU(cudaStreamWaitEvent(e->side, e->ev_start, 0));
-                const unsigned vgrid = (unsigned)(delta ? e->val_grid_delta : e->val_grid);
-                k_val<<<vgrid, CTA_THREADS, 0, e->side>>>(p);
+                k_val<<<(unsigned)e->val_grid, CTA_THREADS, 0, e->side>>>(p);
+                if (e->hard_search) { k_val_hard<<<HARD_CTAS, 32, 0, e->side>>>(p); e->launches++; }
                 CU(cudaEventRecord(e->ev_val, e->side));
                 e->launches++;
                 CU(cudaStreamWaitEvent(s0, e->ev_val, 0));                   // join

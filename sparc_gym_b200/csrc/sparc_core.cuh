@@ -594,9 +594,110 @@ SPARC_HD int fit_step(FitState& f, const SparcShape* shapes, int ns, int code, i
     }
 }
 
+// The plain depth-first search with its whole state in registers (no ordinal / split bookkeeping): what one thread runs
+// for one region in the fused kernel, in k_val and in sparc_validate.  Same tree, same order as fit_init + fit_step with
+// nsplit = 0 (tests/test_exact_fit.py counts the nodes of both).  1 = fits, 0 = does not, -1 = `budget` nodes spent
+// (budget <= 0: unlimited).
+SPARC_HD int exact_fit_budget(uint64_t region, int w, int h, const SparcShape* shapes, int ns,
+                              const Cnt8& n_poly, const Cnt8& n_ylop, int budget) {
+    SPARC_COUNT_FIT_CALL();
+    Cnt8 rem_p = n_poly, rem_y = n_ylop;
+    uint8_t fr_cell[128], fr_q[128];                          // DFS edges: q < 2ns placement, 0xFF = advance
+    int tot_p = 0, tot_y = 0;
+    uint32_t have_p = 0, have_y = 0, mono_slots = 0;
+    bool all_connected = true;
+    // isolated-cell prune: once no ylop is left, a demanded cell with no demanded 4-neighbour can only be
+    // covered by a one-cell poly (every other shape is 4-connected and would need a neighbour)
+    for (int s = 0; s < ns; s++) {
+        const ShapeW sh = load_shape(shapes + s);
+        const int fl = shp_flags(sh.mask);
+        int np = cnt8_get(rem_p, s), ny = cnt8_get(rem_y, s);
+        if (fl & 2) { cnt8_add(rem_p, s, -np); cnt8_add(rem_y, s, -ny); np = ny = 0; }   // zero-area shapes never touch the grid
+        if ((np | ny) && !(sh.anchors & SPARC_CELLS56)) return 0;       // fits nowhere on this board
+        tot_p += np; tot_y += ny;
+        if (np) { have_p |= 1u << s; if (!(fl & 4)) all_connected = false; }
+        if (ny) have_y |= 1u << s;
+        if ((sh.mask & SPARC_CELLS56) == 1ull) mono_slots |= 1u << s;
+    }
+    if (tot_y > SPARC_MAX_YLOPS) return 0;                // (ingest guarantees this never happens)
+    Cnt4 c = {region, 0, 0, 0};
+    uint64_t grid = 0;
+    for (int cx = 0; cx < w; cx++) grid |= ((1ull << h) - 1ull) << (cx * 8);
+    int level = 0, cell = 0, q = 0;
+    if (tot_y == 0) cell = sp_ffsll(region) - 1;              // no ylops: only demanded cells ever matter
+    for (int it = 0;; it++) {
+        if (budget > 0 && it >= budget) return -1;
+        SPARC_COUNT_FIT();
+        const int n = cnt4_get(c, cell);
+        const uint64_t later = grid & ~((2ull << cell) - 1ull);               // cells after `cell`
+        const uint64_t floor_cells = cnt4_eq(c, -tot_y) & later;              // later cells already at what ylops can lift
+        bool found = false;
+        if (q < ns && n + 1 <= tot_p) {                                       // anchor a ylop here (slots >= q)
+            for (uint32_t cand = have_y & (0xFFFFFFFFu << q); cand; cand &= cand - 1) {
+                const int s = sp_ffs(cand) - 1;
+                const uint64_t m = shape_at(load_shape(shapes + s), cell);
+                if (!m) continue;
+                if (floor_cells & ~m) continue;               // one ylop fewer can lift later cells: those at the floor would be lost
+                cnt4_add(c, m); cnt8_add(rem_y, s, -1); tot_y--;
+                if (!cnt8_get(rem_y, s)) have_y &= ~(1u << s);
+                fr_cell[level] = (uint8_t)cell; fr_q[level] = (uint8_t)s; level++;
+                q = s; found = true;
+                break;
+            }
+        }
+        if (!found && n > 0) {                                                // anchor a poly here (slots >= q - ns)
+            const int q2 = q > ns ? q - ns : 0;
+            for (uint32_t cand = q2 < 32 ? have_p & (0xFFFFFFFFu << q2) : 0u; cand; cand &= cand - 1) {
+                const int s = sp_ffs(cand) - 1;
+                const uint64_t m = shape_at(load_shape(shapes + s), cell);
+                if (!m) continue;
+                if (floor_cells & m) continue;                // would sink below what ylops can lift
+                cnt4_sub(c, m); cnt8_add(rem_p, s, -1); tot_p--;
+                if (tot_y == 0 && all_connected) {
+                    const uint64_t D = (c.b0 | c.b1 | c.b2) & ~c.b3;          // cells still demanded
+                    const uint64_t iso = D & ~((D << 1) | (D >> 1) | (D << 8) | (D >> 8));
+                    if (iso) {
+                        int monos = 0;
+                        for (uint32_t ms = mono_slots; ms; ms &= ms - 1) monos += cnt8_get(rem_p, sp_ffs(ms) - 1);
+                        if (sp_popcll(iso) > monos) { cnt4_add(c, m); cnt8_add(rem_p, s, 1); tot_p++; continue; }
+                    }
+                }
+                if (!cnt8_get(rem_p, s)) have_p &= ~(1u << s);
+                fr_cell[level] = (uint8_t)cell; fr_q[level] = (uint8_t)(ns + s); level++;
+                q = ns + s; found = true;
+                break;
+            }
+        }
+        if (found) continue;
+        if (n == 0) {                                                         // settled: advance
+            const uint64_t open = (c.b0 | c.b1 | c.b2 | c.b3) & later;        // later cells with non-zero demand
+            if (tot_p + tot_y == 0) { if (!open) return 1; }               // nothing left and nothing demanded
+            else if (later && (tot_y > 0 || open)) {
+                // with ylops still to place every later cell is a candidate anchor; without, only a
+                // demanded cell can take a poly, so jump straight to the next one
+                fr_cell[level] = (uint8_t)cell; fr_q[level] = 0xFF; level++;
+                cell = sp_ffsll(tot_y > 0 ? later : open) - 1; q = 0;
+                continue;
+            }
+        }
+        for (;;) {                                                            // backtrack
+            if (level == 0) return 0;
+            level--;
+            cell = fr_cell[level];
+            const int qq = fr_q[level];
+            if (qq == 0xFF) continue;                                         // advance was the last child
+            if (qq < ns) { cnt4_sub(c, shape_at(load_shape(shapes + qq), cell)); cnt8_add(rem_y, qq, 1); tot_y++; have_y |= 1u << qq; }
+            else { cnt4_add(c, shape_at(load_shape(shapes + qq - ns), cell)); cnt8_add(rem_p, qq - ns, 1); tot_p++; have_p |= 1u << (qq - ns); }
+            q = qq + 1;
+            break;
+        }
+    }
+}
+
 // one copy of the search: `code` / `nsplit` select its share of the tree (0, 0 = all of it)
 SPARC_HD bool exact_fit(uint64_t region, int w, int h, const SparcShape* shapes, int ns,
                         const Cnt8& n_poly, const Cnt8& n_ylop, int code = 0, int nsplit = 0) {
+    if (nsplit == 0) return exact_fit_budget(region, w, h, shapes, ns, n_poly, n_ylop, 0) != 0;
     FitState f;
     int r = fit_init(f, region, w, h, shapes, ns, n_poly, n_ylop);
     while (r < 0) r = fit_step(f, shapes, ns, code, nsplit);
@@ -608,8 +709,10 @@ SPARC_HD bool exact_fit(uint64_t region, int w, int h, const SparcShape* shapes,
 // region_fit: optional int8[SPARC_MAX_REGIONS], pre-filled with SPARC_FIT_NONE: the poly/ylop verdict of every
 // region (SG.py:674-702); asking for it makes the poly rule look at every region instead of stopping at the
 // first failure.
+// fit_budget > 0: an exact-fit search that needs more nodes makes the call return -1 (k_val: the snapshot becomes a
+// hard item, see k_val_hard).
 SPARC_HD int validate_env(const StoreDev& st, uint32_t puzzle, const uint32_t* vd, int ax, int ay,
-                          int8_t* region_map, int8_t* region_fit = nullptr) {
+                          int8_t* region_map, int8_t* region_fit = nullptr, int fit_budget = 0) {
     VP_BEGIN();
     const HdrRegs h = load_hdr(st, puzzle);
     const uint32_t* nbp = st.nb + (size_t)puzzle * SPARC_N_NODE_BOARDS * 8;
@@ -757,7 +860,11 @@ SPARC_HD int validate_env(const StoreDev& st, uint32_t puzzle, const uint32_t* v
                 int verdict = SPARC_FIT_OK;
                 VP_TIC();
                 if (net != sp_popcll(R)) verdict = SPARC_FIT_AREA_MISMATCH;   // SG.py:679-682
-                else if (!exact_fit(R, w, hh, shapes, h.n_shapes, np, nyl)) verdict = SPARC_FIT_NO_TILING;
+                else {
+                    const int fit = exact_fit_budget(R, w, hh, shapes, h.n_shapes, np, nyl, fit_budget);
+                    if (fit < 0) return -1;
+                    if (!fit) verdict = SPARC_FIT_NO_TILING;
+                }
                 VP_TOC(vp_fit);
                 if (verdict != SPARC_FIT_OK) poly_ok = false;
                 if (region_fit && rid < SPARC_MAX_REGIONS) region_fit[rid] = (int8_t)verdict;
@@ -1107,6 +1214,13 @@ struct KParams {
     SparcObsOut obs;
     uint32_t* vq_count;      // deferred terminal validation: number of queued envs (nullptr = validate inline)
     uint32_t* vq;            // [n_envs][SPARC_VQ_WORDS]: env, puzzle, x | y << 8, pad, visited[8]
+    uint32_t* hq_count;      // hard items: snapshots whose exact-fit search outgrew the validator's node budget (k_val_hard)
+#if defined(__CUDACC__)
+    uint4* hq;
+#else
+    void* hq;
+#endif
+    int fit_budget;          // nodes an inline exact-fit search may visit before the snapshot becomes a hard item (0 = no limit)
     uint32_t* rq_count;      // delta observations: number of envs that began a new episode this step (nullptr in the
     uint32_t* rq;            // fused kernel, which decides per tile); [n_envs] their indices -> k_encode_list
 };
@@ -1251,15 +1365,18 @@ SPARC_HD bool phase_a(const KParams& p, long long i, EnvRegs& e, uint32_t* scrat
     return have_stats;
 }
 
-// deferred terminal validation of queue entry `slot`: writes the env's rule flags, returns 1 when
-// all rules are satisfied (for the RULES_PASS statistic)
-SPARC_HD int validate_queued(const KParams& p, uint32_t slot) {
+// deferred terminal validation of queue entry `slot` (one thread): writes the env's rule flags, returns 1 when all
+// rules are satisfied (for the RULES_PASS statistic), 0 when not, -1 when an exact-fit search outgrew `fit_budget`
+// (nothing written: the snapshot becomes a hard item)
+SPARC_HD int validate_queued(const KParams& p, uint32_t slot, int fit_budget = 0) {
     const uint32_t* q = p.vq + (size_t)slot * SPARC_VQ_WORDS;
     uint32_t vd[SPARC_DYN_STRIDE];
 #pragma unroll
     for (int k = 0; k < 8; k++) vd[k] = q[4 + k];
     vd[8] = 0;
-    const int f = validate_env(p.st, q[1], vd, (int)(q[2] & 0xff), (int)((q[2] >> 8) & 0xff), nullptr) | SPARC_RULE_VALID;
+    int f = validate_env(p.st, q[1], vd, (int)(q[2] & 0xff), (int)((q[2] >> 8) & 0xff), nullptr, nullptr, fit_budget);
+    if (f < 0) return -1;
+    f |= SPARC_RULE_VALID;
     if (p.out.rule_flags_dev) p.out.rule_flags_dev[q[0]] = (uint16_t)f;
     return (f & SPARC_RULE_ALL) != 0;
 }
