@@ -50,8 +50,11 @@ def measured_peaks():
 def ncu_traffic(workload, n_env):
     """dram__bytes_read.sum + dram__bytes_write.sum per k_env launch from the committed `ncu --set full` capture of
     this workload (profiles/r1_traffic.json), or None when the capture does not match the run."""
-    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    if not os.path.exists(p):
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(p):
+            break
+    else:
         return None
     with open(p) as f:
         t = json.load(f).get(workload)
@@ -275,6 +278,9 @@ def main():
     ap.add_argument("--obs-update", default="rewrite", choices=["rewrite", "delta"],
                     help="rewrite = every step writes every observation in full (the headline); delta = the persistent "
                          "observation is touched in place, full rewrite only for envs that begin a new episode")
+    ap.add_argument("--obs-to-host", action="store_true",
+                    help="also time steps whose WHOLE observation is copied to pinned host memory (what a host-side consumer "
+                         "of the reference's API receives); reported under `obs_to_host`, never the headline")
     ap.add_argument("--no-graph", action="store_true", help="launch every step from Python instead of one CUDA graph of K steps")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
@@ -416,6 +422,32 @@ def main():
                "api": "SparcVecEnv.step_host -> sparc_step_host (pinned host actions in; reward f32 + terminated u8 + "
                       "truncated u8 out; observation tensors stay on the device for the policy)"}
 
+    # ---- the whole observation to the host, every step (a host consumer; PCIe-bound)
+    obs_host = None
+    if (args.obs_to_host or (world == 1 and args.workload == "config4" and not args.no_extra)) and not args.no_obs:
+        host = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in env.obs.items()}
+        nbytes = sum(v.numel() * v.element_size() for v in host.values())
+        K2 = max(3, min(K, 8))
+        for t in range(2):
+            env.step(actions[t])
+            for k in host:
+                host[k].copy_(env.obs[k], non_blocking=True)
+        barrier()
+        ev0.record()
+        for t in range(K2):
+            env.step(actions[W + t % K])
+            for k in host:
+                host[k].copy_(env.obs[k], non_blocking=True)     # same stream: the next step may not overwrite what is being copied
+        ev1.record()
+        barrier()
+        oh_ms = ev0.elapsed_time(ev1) / K2
+        obs_host = {"value": round(n_env * world / (oh_ms / 1e3), 1), "unit": "env-steps/s", "ms_per_step": round(oh_ms, 4),
+                    "d2h_bytes_per_step": nbytes * world, "d2h_GBs_per_gpu": round(nbytes / (oh_ms / 1e3) / 1e9, 2), "steps": K2,
+                    "obs_format": args.obs_format,
+                    "note": "step + cudaMemcpyAsync of base / color / additional_info into pinned host tensors, one stream; bound by "
+                            "the host link, not by the kernels"}
+        del host
+
     if sampler and not args.no_e2e:
         # keep the GPU under the same load for ~1.5 s so that nvidia-smi (100 ms period) sees it
         t_end = time.perf_counter() + 1.5
@@ -443,8 +475,13 @@ def main():
         step_ms = ms_max / K
         fused = launches == K                      # small batches: the single fused kernel k_env is the step
         kernel_ms = step_ms if (fused or enc_ms is None) else enc_ms
-        achieved = b_alg * n_env / (kernel_ms / 1e3) / 1e9
+        # the dominant kernel's OWN algorithmic bytes: k_encode writes the observation and reads 16 + 4*nv + 4 bytes of
+        # state per env; it neither writes state nor touches actions / rewards (those belong to k_dyn and are in b_alg)
+        S = st.slab_x * st.slab_y
+        k_bytes = b_alg if (fused or enc_ms is None) else (b_alg - 208) + 16 + 4 * ((S + 31) // 32) + 4
+        achieved = k_bytes * n_env / (kernel_ms / 1e3) / 1e9
         step_achieved = b_alg * n_env / (step_ms / 1e3) / 1e9
+        write_peak = 7250.0          # tools/write_peak.py: 1.15 GB memset on a B200 of this pool (a write-only stream beats the copy figure)
         line = {
             "metric": "env-steps/sec (whole box)", "value": round(value, 1), "unit": "env-steps/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": round(ms_max / K, 5),
@@ -464,15 +501,23 @@ def main():
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": ncu_traffic(args.workload, n_env) if (args.obs_format == "reference" and args.obs_update == "rewrite") else None, "peak_source": peak_src,
                          "kernel": "k_env (fused step)" if fused else
-                                   "the whole step = k_dyn (dynamics + in-place observation update), then k_val || k_encode_list" if args.obs_update == "delta" else
+                                   "the whole step = k_dyn (dynamics + in-place observation update), then k_post (terminal validation + rewrite of the envs that began a new episode)" if args.obs_update == "delta" else
                                    "k_encode (state -> observation; the step = k_dyn, then k_val || k_encode)",
-                         "algorithmic_bytes_per_env_step": b_alg, "envs_per_launch": n_env,
+                         "algorithmic_bytes_per_env_step": k_bytes, "envs_per_launch": n_env,
+                         "bytes_note": ("the kernel's own bytes: observation written + state read" if k_bytes != b_alg else
+                                        "whole-step bytes (SURVEY 8d): observation + state read and written + io"),
                          "kernel_ms": round(kernel_ms, 5), "share_of_step": round(kernel_ms / step_ms, 4),
+                         "frac_of_write_only_ceiling": round(achieved / write_peak, 4),
                          "whole_step": {"achieved": round(step_achieved, 1), "frac": round(step_achieved / peak, 4),
-                                        "ms": round(step_ms, 5)},
-                         "write_only_ceiling_GBs": 7250.0},
+                                        "ms": round(step_ms, 5), "algorithmic_bytes_per_env_step": b_alg,
+                                        "frac_of_write_only_ceiling": round(step_achieved / write_peak, 4)},
+                         "write_only_ceiling_GBs": write_peak,
+                         "note": "a write-only stream exceeds the measured COPY bandwidth (peak): frac can pass 1; "
+                                 "frac_of_write_only_ceiling is against the measured memset rate"},
             "episode_stats": stats,
         }
+        if obs_host is not None:
+            line["obs_to_host"] = obs_host
         if world == 1 and args.workload == "config4" and not args.no_extra and not args.no_obs:
             # BASELINE configs[1] (4,096 envs, 4x4 gaps+dots: a launch/latency-bound batch) measured in the same
             # run, for reference; the headline stays the configuration the north-star target is quoted on
@@ -489,16 +534,16 @@ def main():
                 line["other_workloads"] = {"config2": {"error": res.stderr[-200:]}}
             # the same workload in the compact observation format (uint8 / uint8 / int32), under its OWN algorithmic bytes
             res = subprocess.run([sys.executable, os.path.abspath(__file__), "--workload", args.workload, "--steps", "300",
-                                  "--warmup", "20", "--no-cpu-baseline", "--no-extra", "--no-e2e", "--obs-format", "compact"],
+                                  "--warmup", "20", "--no-cpu-baseline", "--no-extra", "--no-e2e", "--obs-format", "compact", "--obs-to-host"],
                                  capture_output=True, text=True)
             try:
                 j3 = json.loads(res.stdout.strip().splitlines()[-1])
                 line["other_workloads"][args.workload + "_compact_obs"] = {
                     "description": "same envs and puzzles, observation in uint8 planes / uint8 colour / int32 additional_info",
                     "value": j3["value"], "unit": j3["unit"], "ms_per_step": j3["ms_per_step"],
-                    "algorithmic_bytes_per_env_step": j3["roofline"]["algorithmic_bytes_per_env_step"],
+                    "algorithmic_bytes_per_env_step": j3["roofline"]["whole_step"]["algorithmic_bytes_per_env_step"],
                     "roofline_frac_whole_step": j3["roofline"]["whole_step"]["frac"],
-                    "roofline_frac_encoder": j3["roofline"]["frac"]}
+                    "roofline_frac_encoder": j3["roofline"]["frac"], "obs_to_host": j3.get("obs_to_host")}
             except Exception:
                 line["other_workloads"][args.workload + "_compact_obs"] = {"error": res.stderr[-200:]}
             # the same workload with the observation updated in place (reference dtypes), under its OWN algorithmic bytes
@@ -511,9 +556,9 @@ def main():
                     "description": "same envs and puzzles, the persistent observation touched in place (visited / agent_location "
                                    "cells), envs that begin a new episode rewritten in full; same tensor contents after every step",
                     "value": j4["value"], "unit": j4["unit"], "ms_per_step": j4["ms_per_step"],
-                    "algorithmic_bytes_per_env_step": j4["roofline"]["algorithmic_bytes_per_env_step"],
+                    "algorithmic_bytes_per_env_step": j4["roofline"]["whole_step"]["algorithmic_bytes_per_env_step"],
                     "roofline_frac_whole_step": j4["roofline"]["whole_step"]["frac"],
-                    "note": "latency-bound (k_dyn, then the terminal validation k_val), not HBM-bound"}
+                    "note": "latency-bound (k_dyn, then k_post: terminal validation + new-episode rewrites), not HBM-bound"}
             except Exception:
                 line["other_workloads"][args.workload + "_delta_obs"] = {"error": res.stderr[-200:]}
         if not args.no_cpu_baseline and world == 1:
