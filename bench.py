@@ -31,6 +31,9 @@ sys.path.insert(0, ROOT)
 
 WORKLOADS = {
     # name: (config id, envs per GPU, pool size, traceback, max_steps, description)
+    # BASELINE configs[0]: the reference's own CPU-runnable case; through the N=1 Gymnasium drop-in (--workload config1
+    # times sparc_gym_b200.make(...).step(), one env, host in / host out: see dropin_bench)
+    "config1": (1, 1, 1, False, 1000, "single 4x4 gaps+dots puzzle, random-action rollout via the gym.make surface (one env)"),
     "config2": (2, 4096, 64, False, 1000, "4,096 lockstep envs, 4x4 gaps+dots puzzles (9x9 lattice, 5 planes)"),
     "config3": (3, 65536, 1024, True, 1000, "65,536 envs, mixed 3x3-6x6 full-rule puzzles padded to 13x13, traceback, terminal validation"),
     "config4": (4, 131072, 4096, False, 1000, "131,072 envs per GPU (1M on 8 GPUs), 6x6 full rule set, 8 colours (13x13 lattice, 10 planes)"),
@@ -180,11 +183,11 @@ class CpuArm:
         import refharness as rh
         cfg, _, _, traceback, max_steps, _ = WORKLOADS[workload]
         self.workload = workload
-        self.cores = cores or os.cpu_count() or 1
+        self.cores = 1 if cfg == 1 else (cores or os.cpu_count() or 1)      # config 1 is ONE env (gym.make, no vectorisation)
         self.kind = kind or ("reference" if rh.reference_available() else "port")
         self.ref_root = rh.REFERENCE_ROOT if self.kind == "reference" else None
         rows = config_pool(cfg, n_puzzles=8 * self.cores)
-        by_worker = [rows[8 * w:8 * w + 8] for w in range(self.cores)]
+        by_worker = [rows] if cfg == 1 else [rows[8 * w:8 * w + 8] for w in range(self.cores)]
         ctx = mp.get_context("fork")
         self.pool = ctx.Pool(self.cores, initializer=_cpu_worker_init,
                              initargs=(by_worker, traceback, max_steps, self.kind, ctx.Value("i", 0)))
@@ -227,6 +230,33 @@ def cpu_baseline(workload, budget_s=10.0, samples=1, warmup=0, kind=None, cores=
         out["port_note"] = ("the oracle port (reference_cost=True) on the same puzzles and cores, one sample: "
                             "%.2fx the unmodified reference" % (r / max(out["value"], 1e-9)))
     return out
+
+
+def dropin_bench(n_steps=10000, warmup=500, touch_info=False, device="cuda:0"):
+    """BASELINE configs[0] through the reference's own call surface: gym.make('SPaRc-Gym', observation='new',
+    traceback=False, max_steps=1000) -> reset / step(action) with a Python int in and (obs dict of numpy planes, reward,
+    terminated, truncated, info) out, one env, every step a full round trip to the GPU.  touch_info: also read
+    info['rule_status'] every step (the lazy part of the drop-in's info)."""
+    import sparc_gym_b200
+    from sparc_gym_b200.dataset import config_pool
+    row = config_pool(1)[0]
+    env = sparc_gym_b200.make("SPaRc-Gym", puzzles=[row], observation="new", traceback=False, max_steps=1000, device=device)
+    acts = np.random.default_rng(0).integers(0, 4, n_steps + warmup).tolist()
+    env.reset(options={"puzzle_id": row["id"]})
+    episodes, t0 = 0, 0.0
+    for t, a in enumerate(acts):
+        if t == warmup:
+            t0 = time.perf_counter()
+        obs, r, te, tr, info = env.step(a)
+        if touch_info:
+            info["rule_status"]
+        if te or tr:
+            episodes += 1
+            env.reset(options={"puzzle_id": row["id"]})
+    dt = time.perf_counter() - t0
+    env.close()
+    return {"value": round(n_steps / dt, 1), "unit": "env-steps/s", "us_per_step": round(1e6 * dt / n_steps, 2), "steps": n_steps,
+            "episodes": episodes, "rule_status_read_every_step": touch_info}
 
 
 def workload_config(args, world, store=None):
@@ -278,6 +308,10 @@ def main():
     ap.add_argument("--obs-update", default="rewrite", choices=["rewrite", "delta"],
                     help="rewrite = every step writes every observation in full (the headline); delta = the persistent "
                          "observation is touched in place, full rewrite only for envs that begin a new episode")
+    ap.add_argument("--stats-every", type=int, default=0,
+                    help="also time the steps (launched from Python, no graph) with the episode statistics reduced over all ranks "
+                         "every K steps on a side stream (ShardedRunner.stats_async) inside the timed region; reported under "
+                         "`stats_collective` beside the same loop without it")
     ap.add_argument("--obs-to-host", action="store_true",
                     help="also time steps whose WHOLE observation is copied to pinned host memory (what a host-side consumer "
                          "of the reference's API receives); reported under `obs_to_host`, never the headline")
@@ -313,6 +347,28 @@ def main():
     import torch.distributed as dist
     from sparc_gym_b200.dataset import config_pool
     from sparc_gym_b200.runner import ShardedRunner, reduce_stats
+
+    if args.workload == "config1":                                  # the N=1 drop-in, wall-clock (one env cannot fill a GPU)
+        if rank != 0:
+            return
+        assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+        fast, eager = dropin_bench(touch_info=False), dropin_bench(touch_info=True)
+        line = {"metric": "env-steps/sec (whole box)", "value": fast["value"], "unit": "env-steps/s", "n_gpus": 1,
+                "steps": fast["steps"], "warmup": 500, "ms_per_step": round(fast["us_per_step"] / 1e3, 5), "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+                "config": {"workload": "config1", "description": WORKLOADS["config1"][5], "traceback": False, "max_steps": 1000,
+                           "api": "sparc_gym_b200.make('SPaRc-Gym', ...).step(a): one env, host in / host out, wall clock"},
+                "dropin": fast, "dropin_rule_status_read": eager}
+        if not args.no_cpu_baseline:
+            res = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", "config1",
+                                  "--steps", "2", "--warmup", "1", "--cpu-seconds", "4", "--no-extra"], capture_output=True, text=True)
+            try:
+                line["cpu_baseline"] = json.loads(res.stdout.strip().splitlines()[-1])["cpu_baseline"]
+                line["vs_reference_env_1core"] = round(fast["value"] / line["cpu_baseline"]["value"], 2)
+            except Exception:
+                line["cpu_baseline"] = {"error": res.stderr[-300:]}
+        print(json.dumps(line))
+        return
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
@@ -422,6 +478,36 @@ def main():
                "api": "SparcVecEnv.step_host -> sparc_step_host (pinned host actions in; reward f32 + terminated u8 + "
                       "truncated u8 out; observation tensors stay on the device for the policy)"}
 
+    # ---- the statistics collective inside the loop: K steps from Python with and without stats_async
+    stats_coll = None
+    if args.stats_every > 0:
+        def loop():
+            barrier()
+            ev0.record()
+            for t in range(W, W + K):
+                runner.step(actions[t])
+            ev1.record()
+            barrier()
+            t_ = torch.tensor([ev0.elapsed_time(ev1) / K], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+            return float(t_.item())
+        for t in range(3):
+            runner.step(actions[t])
+        base_ms = min(loop(), loop())
+        a = runner.stats_async(every=args.stats_every)
+        for t in range(args.stats_every):
+            runner.step(actions[t])                  # first reduction (communicator set-up) outside the timed region
+        a.latest(wait=True)
+        with_ms = min(loop(), loop())
+        got = a.latest(wait=True)
+        runner._async = None
+        stats_coll = {"every": args.stats_every, "ms_per_step_without": round(base_ms, 5), "ms_per_step_with": round(with_ms, 5),
+                      "overhead_frac": round(with_ms / base_ms - 1.0, 4), "reductions": a.reductions,
+                      "latest_tick": got[0] if got else None, "latest_episodes": got[1]["episodes"] if got else None,
+                      "how": "K steps launched from Python (no CUDA graph), max over ranks, best of 2; every `every` steps k_read_stats + "
+                             "all_reduce(int64[8]) on a side stream through a process group of its own (NCCL over NVLink)"}
+
     # ---- the whole observation to the host, every step (a host consumer; PCIe-bound)
     obs_host = None
     if (args.obs_to_host or (world == 1 and args.workload == "config4" and not args.no_extra)) and not args.no_obs:
@@ -518,6 +604,8 @@ def main():
         }
         if obs_host is not None:
             line["obs_to_host"] = obs_host
+        if stats_coll is not None:
+            line["stats_collective"] = stats_coll
         if world == 1 and args.workload == "config4" and not args.no_extra and not args.no_obs:
             # BASELINE configs[1] (4,096 envs, 4x4 gaps+dots: a launch/latency-bound batch) measured in the same
             # run, for reference; the headline stays the configuration the north-star target is quoted on
@@ -532,6 +620,16 @@ def main():
                     "note": "11.5 MB of observation per step: L2-resident and launch/latency bound, not HBM bound"}}
             except Exception:
                 line["other_workloads"] = {"config2": {"error": res.stderr[-200:]}}
+            # BASELINE configs[0] through the gym.make surface (one env, host in / host out), beside the reference env on one core
+            res = subprocess.run([sys.executable, os.path.abspath(__file__), "--workload", "config1"], capture_output=True, text=True)
+            try:
+                j1 = json.loads(res.stdout.strip().splitlines()[-1])
+                line["other_workloads"]["config1_dropin"] = {
+                    "description": j1["config"]["description"], "api": j1["config"]["api"], "value": j1["value"], "unit": j1["unit"],
+                    "us_per_step": j1["dropin"]["us_per_step"], "with_rule_status_read_every_step": j1["dropin_rule_status_read"]["value"],
+                    "reference_env_1core": j1.get("cpu_baseline", {}).get("value"), "vs_reference_env_1core": j1.get("vs_reference_env_1core")}
+            except Exception:
+                line["other_workloads"]["config1_dropin"] = {"error": (res.stderr or res.stdout)[-200:]}
             # the same workload in the compact observation format (uint8 / uint8 / int32), under its OWN algorithmic bytes
             res = subprocess.run([sys.executable, os.path.abspath(__file__), "--workload", args.workload, "--steps", "300",
                                   "--warmup", "20", "--no-cpu-baseline", "--no-extra", "--no-e2e", "--obs-format", "compact", "--obs-to-host"],

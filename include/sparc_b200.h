@@ -68,7 +68,11 @@ enum { SPARC_RULE_REACHED_TARGET = 1 << 0, SPARC_RULE_PATH_NOT_CROSSING = 1 << 1
 
 /* autoreset modes (no reference counterpart: the reference is single-env and never guards a
  * finished episode) */
-enum { SPARC_AUTORESET_DISABLED = 0, SPARC_AUTORESET_NEXT_STEP = 1, SPARC_AUTORESET_SAME_STEP = 2 };
+enum { SPARC_AUTORESET_DISABLED = 0, SPARC_AUTORESET_NEXT_STEP = 1, SPARC_AUTORESET_SAME_STEP = 2,
+       SPARC_AUTORESET_CONTINUE = 3 /* the reference's own behaviour (SG.py:1131-1238 has no guard): a finished
+                                       episode is stepped like a live one -- the agent keeps moving, every further step
+                                       returns +-1.  Used by the single-env drop-in; episode statistics then count every
+                                       such step as an episode end. */ };
 /* when the rule validator runs inside sparc_step */
 enum { SPARC_VALIDATE_NEVER = 0, SPARC_VALIDATE_TERMINAL = 1, SPARC_VALIDATE_EVERY_STEP = 2 };
 /* action dtypes accepted by sparc_step */
@@ -239,6 +243,19 @@ int sparc_stats(SparcEnv* env, int64_t* out_dev, int clear, void* stream);
 int sparc_step_host(SparcEnv* env, const uint8_t* actions_host, float* reward_host,
                     uint8_t* terminated_host, uint8_t* truncated_host,
                     const SparcObsOut* obs, void* stream);
+
+/* HOST-record step / reset: what the single-env Gymnasium drop-in needs after every call, in ONE device->host copy
+ * (the reference's step() returns info with legal actions, step counter, agent location and the rule status of the
+ * CURRENT state, SG.py:994-1022): steps (or resets) all envs, validates every env's current state (flags, region
+ * map, per-region poly/ylop verdicts: sparc_validate), copies the record below into `record_host` and synchronises
+ * `stream`.  actions_host / puzzle_idx_host: int32[n_envs] in host memory (puzzle_idx_host may be NULL = keep).
+ * Record, struct of arrays over the n envs, sparc_info_record_bytes(env) bytes:
+ *   int32 step[n] | uint16 flags[n] (SPARC_RULE_* | SPARC_RULE_VALID) | uint8 agent_xy[n][2] | int8 reward_code[n] |
+ *   uint8 terminated[n] | uint8 truncated[n] | uint8 legal_mask[n] | int8 region_fit[n][SPARC_MAX_REGIONS] |
+ *   int8 region_map[n][slab_x][slab_y] */
+int64_t sparc_info_record_bytes(const SparcEnv* env);
+int sparc_step_info_host(SparcEnv* env, const int32_t* actions_host, void* record_host, const SparcObsOut* obs, void* stream);
+int sparc_reset_info_host(SparcEnv* env, const int32_t* puzzle_idx_host, void* record_host, const SparcObsOut* obs, void* stream);
 
 /* checkpoint / restore of the per-env state: opaque blob of
  * sparc_state_bytes(env) bytes, device memory. */

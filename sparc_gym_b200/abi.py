@@ -26,15 +26,15 @@ STAT_NAMES = ("episodes", "solved", "failed", "truncated", "steps", "return_cent
 RULE_VALID = 1 << 15
 MAX_REGIONS = 64                              # SPARC_MAX_REGIONS
 FIT_NONE, FIT_AREA_MISMATCH, FIT_NO_TILING, FIT_OK = 0, 1, 2, 3   # SPARC_FIT_*: per-region poly/ylop verdicts
-AUTORESET = {"disabled": 0, "next_step": 1, "same_step": 2}
+AUTORESET = {"disabled": 0, "next_step": 1, "same_step": 2, "continue": 3}   # continue: the reference's no-guard stepping (Q4)
 VALIDATE = {"never": 0, "terminal": 1, "every_step": 2}
 ACT_DTYPES = {"uint8": 0, "int32": 1, "int64": 2}
 REWARD_VALUES = (0, 0.01, -0.01, 1, -1)      # reward code -> the reference's Python value (SG.py:1204-1223)
 
 EXPORTS = ("sparc_abi_version", "sparc_last_error", "sparc_store_create", "sparc_store_destroy",
            "sparc_env_create", "sparc_env_destroy", "sparc_reset", "sparc_step", "sparc_encode", "sparc_validate",
-           "sparc_stats", "sparc_step_host", "sparc_state_bytes", "sparc_state_save",
-           "sparc_state_load", "sparc_env_num_envs", "sparc_kernel_launches")
+           "sparc_stats", "sparc_step_host", "sparc_info_record_bytes", "sparc_step_info_host", "sparc_reset_info_host",
+           "sparc_state_bytes", "sparc_state_save", "sparc_state_load", "sparc_env_num_envs", "sparc_kernel_launches")
 
 
 class SparcError(RuntimeError):
@@ -110,6 +110,10 @@ def load_library():
     lib.sparc_validate.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.sparc_stats.argtypes = [vp, vp, i32, vp]
     lib.sparc_step_host.argtypes = [vp, vp, vp, vp, vp, C.POINTER(ObsOut), vp]
+    lib.sparc_info_record_bytes.argtypes = [vp]
+    lib.sparc_info_record_bytes.restype = i64
+    lib.sparc_step_info_host.argtypes = [vp, vp, vp, C.POINTER(ObsOut), vp]
+    lib.sparc_reset_info_host.argtypes = [vp, vp, vp, C.POINTER(ObsOut), vp]
     lib.sparc_state_bytes.argtypes = [vp]
     lib.sparc_state_bytes.restype = i64
     lib.sparc_state_save.argtypes = [vp, vp, vp]

@@ -126,7 +126,7 @@ struct StateDev {
     unsigned long long* stats;     // [SPARC_N_STATS]
 };
 
-enum { FL_DONE = 1, FL_TERM = 2, FL_TRUNC = 4 };
+enum { FL_DONE = 1, FL_TERM = 2, FL_TRUNC = 4, FL_WON = 8 /* autoreset CONTINUE only: the last final step was a win */ };
 #define SPARC_MOVE_WORDS 12
 
 struct EnvRegs {                   // one env's state in registers
@@ -299,11 +299,17 @@ SPARC_HD void env_step(EnvRegs& e, const StoreDev& st, const StateDev& sd, const
     if (terminated) truncated = 0;                         // SG.py:1198-1199
     const int on_trie = (e.on_depth == plen) && e.tnode != 0;
     int code = SPARC_R_ZERO;
+    const bool keep_going = cfg.autoreset == SPARC_AUTORESET_CONTINUE;
     if (terminated || truncated) {                         // SG.py:1204-1213
         const int is_end = on_trie ? (int)sp_ldg(st.trie + (size_t)e.tnode * SPARC_TRIE_NODE_WORDS + 5) : 0;
         code = is_end ? SPARC_R_WIN : SPARC_R_LOSE;
-    } else if (moved && (h.flags & 1)) {                   // SG.py:1214-1223
-        code = on_trie ? SPARC_R_ON_PATH : SPARC_R_OFF_PATH;
+        // stepping past the end (the reference has no guard, Q4): its outcome_reward is only cleared by a
+        // non-final step, so once it is 1 a later final step that is not on a listed path leaves it alone and
+        // returns the normal reward of that step, 0 (SG.py:1205-1213: `if self.outcome_reward != 1`)
+        if (keep_going) { if (is_end) e.flags |= FL_WON; else if (e.flags & FL_WON) code = SPARC_R_ZERO; }
+    } else {
+        if (keep_going) e.flags &= ~FL_WON;
+        if (moved && (h.flags & 1)) code = on_trie ? SPARC_R_ON_PATH : SPARC_R_OFF_PATH;   // SG.py:1214-1223
     }
     e.ep_ret += (code == SPARC_R_ON_PATH) - (code == SPARC_R_OFF_PATH) + 100 * ((code == SPARC_R_WIN) - (code == SPARC_R_LOSE));
     r.reward_code = code; r.terminated = terminated; r.truncated = truncated; r.legal_mask = legal_after;
@@ -1330,6 +1336,8 @@ SPARC_HD bool phase_a(const KParams& p, long long i, EnvRegs& e, uint32_t* scrat
                 env_reset(e, st, (e.puzzle + (uint32_t)p.cfg.stride) % (uint32_t)st.n_puzzles);
                 need_legal = true;
                 new_episode = true;
+            } else if (p.cfg.autoreset == SPARC_AUTORESET_CONTINUE) {
+                // the reference has no guard (Q4): the episode goes on, the next step is a live step again
             } else {
                 e.flags = FL_DONE | (r.terminated ? FL_TERM : 0) | (r.truncated ? FL_TRUNC : 0);
             }

@@ -12,9 +12,22 @@ All dynamics, rewards, rule validation and the observation planes come from the 
 (one env on the GPU); this class only converts device arrays into the reference's containers.
 `info['rule_status'][rule]['detail']` (SG.py:488-710) is assembled on the host from what the
 device returns: the rule flags, the region map and the per-region poly/ylop verdicts.
-Deliberate differences: resets are clean and there are no pygame renderers.
 observation='SPaRC' (the JSON text grid, SG.py:1149-1184) is assembled on the host from the
 device's dynamics.
+
+One step = ONE call into the library (sparc_step_info_host: action in, dynamics, validation of the new state, one
+packed record out); the numpy planes are touched in place where the agent moved (as SG.py:1146-1188 does) instead
+of being copied from the device, and `info['rule_status']` -- nine `detail` payloads and the region summaries,
+the bulk of the reference's own step time -- is a lazy mapping filled in from a snapshot of that step when it is
+first looked at.
+
+Deliberate differences from the reference:
+* resets are clean (SURVEY Q1: the reference leaks `visited` / `agent_location` across episodes of one puzzle);
+* there are no pygame windows: `render_mode` is accepted as in the reference ('human', 'llm', anything else means no
+  renderer, SG.py:68-74), `render()` draws the board as text -- printed for 'human', returned for 'llm' (the
+  reference's render() docstring promises a text for 'llm'; its pygame renderers return None);
+* like the reference, step() does NOT guard a finished episode (Q4): the agent keeps moving and every further step
+  returns +-1 (tests/golden/postdone.json.gz, recorded from the reference).
 """
 from __future__ import annotations
 
@@ -63,81 +76,63 @@ def _load_rows(df_name, df_split, df_set):
     return load_dataset(df_name, df_split, split=df_set).to_pandas().to_dict("records")
 
 
-class SPaRC_Gym(_Env):
-    metadata = {"render_modes": ["human", "llm"], "render_fps": 30}            # SG.py:45
+class _LazyInfo(dict):
+    """`info` of one step.  'rule_status' is computed from the step's snapshot the first time anything but the cheap
+    keys is looked at (the nine `detail` payloads and the region summaries cost more Python time than the rest of the
+    step); afterwards this is a plain dict with the reference's key order (SG.py:1012-1021)."""
+    __slots__ = ("_snap",)
+    _PENDING = object()
 
-    def __init__(self, df_name="lkaesberg/SPaRC", df_split="all", df_set="test", render_mode=None,
-                 observation="new", traceback=False, max_steps=2000, *, puzzles=None, device="cuda:0"):
-        if observation not in ("new", "SPaRC"):
-            raise ValueError("Invalid observation type. Choose 'new' or 'SPaRC'.")     # SG.py:207
-        if render_mode is not None:
-            raise ValueError("the B200 environment has no renderers (render_mode must be None)")
-        from .vec_env import SparcVecEnv
-        self.render_mode, self.observation = render_mode, observation
-        self.traceback, self.max_steps = traceback, max_steps
-        rows = puzzles if puzzles is not None else _load_rows(df_name, df_split, df_set)
-        if rows is None or len(rows) == 0:
-            raise ValueError("No valid dataframe provided")                    # SG.py:86-87
-        self.puzzles = ingest_rows(rows, observation)
-        self._store = PuzzleStore(self.puzzles)
-        self._vec = SparcVecEnv(self._store, 1, traceback=traceback, max_steps=max_steps,
-                                autoreset_mode="disabled", validate="never", device=device)   # _pull() validates on demand
-        self.current_puzzle_index = 0
-        self.current_step = 0
-        self.rule_status = {}
-        self.action_space = _spaces.Discrete(4)                                # SG.py:210
-        self._load_puzzle(0)                                                   # SG.py:90
+    def __init__(self, items, snap):
+        super().__init__(items)
+        self._snap = snap
 
-    # -- device -> reference containers
-    def _load_puzzle(self, index):
-        import torch
-        pz = self.puzzles[index]
-        self._pz = pz
-        self.x_size, self.y_size = pz.X, pz.Y
-        self.difficulty, self.polyshapes = pz.difficulty, pz.polyshapes
-        self.solution_paths, self.solution_count = pz.solution_paths, pz.solution_count
-        self.start_location, self.target_location = pz.start, pz.target
-        self.normal_reward = 0
-        self.outcome_reward = 0
-        self._vec.reset(puzzle_idx=torch.tensor([index], dtype=torch.int32))
-        # fresh containers per load, then updated in place while the episode runs (SG.py:149-151, 979)
-        self.obs_array = {k: np.zeros((pz.X, pz.Y), np.int32) for k in pz.keys}
-        self.color_array = np.zeros((pz.X, pz.Y), np.int32)
-        self.additional_info = np.zeros((pz.X, pz.Y), np.int64)
-        self._agent_location = np.zeros(2, np.int32)
-        self._target_location = np.array(pz.target, dtype=np.int32)
-        self._pull()
-        if self.observation == "SPaRC":                                        # SG.py:153-164, 198-204
-            self.observ = [[str(c) for c in row] for row in pz.observ]
-            if any(len(r) != len(self.observ[0]) for r in self.observ):
-                raise ValueError("Non-rectangular SPaRC grid")
-            init_json = self._build_json_obs()
-            self.observation_space = _spaces.Text(max_length=int(len(init_json) * 2),
-                                                  charset="".join(sorted(set(init_json) | set("LV."))))
-            return
-        keys = list(self.obs_array.keys())
-        self.observation_space = _spaces.Dict({                                # SG.py:190-196
-            "base": _spaces.Dict({k: _spaces.Box(low=0, high=1, shape=(pz.X, pz.Y), dtype=np.int32) for k in keys}),
-            "color": _spaces.Box(low=0, high=8, shape=(pz.X, pz.Y), dtype=np.int32),
-            "additional_info": _spaces.Box(low=0, high=143632, shape=(pz.X, pz.Y), dtype=np.int64)})
+    def _fill(self):
+        snap, self._snap = self._snap, None
+        if snap is not None:
+            dict.__setitem__(self, "rule_status", snap.rule_status())
 
-    def _pull(self):
-        """Copy the device results of the last reset/step into the reference's containers."""
-        v, st, pz = self._vec, self._store, self._pz
-        flags, rmap, rfit = v.validate(region_map=True, region_fit=True)
-        base = v.obs["base"][0].cpu().numpy()
-        for pi, key in enumerate(st.plane_keys):
-            if key in self.obs_array:
-                self.obs_array[key][...] = base[pi, :pz.X, :pz.Y]
-        self.color_array[...] = v.obs["color"][0, :pz.X, :pz.Y].cpu().numpy()
-        self.additional_info[...] = v.obs["additional_info"][0, :pz.X, :pz.Y].cpu().numpy()
-        self._agent_location[...] = v.agent_xy[0].cpu().numpy()
-        self.current_step = int(v.step_count[0])
-        self._legal = [a for a in range(4) if (int(v.legal_mask[0]) >> a) & 1]
-        f = int(flags[0]) & 0xFFFF
-        self._flags = {name: bool((f >> k) & 1) for k, name in enumerate(RULE_NAMES)}
-        self._region_map = rmap[0, :pz.X, :pz.Y].cpu().numpy()
-        self._region_fit = rfit[0].cpu().numpy()
+    def __getitem__(self, key):
+        if key == "rule_status" and self._snap is not None:
+            self._fill()
+        return dict.__getitem__(self, key)
+
+    def get(self, key, default=None):
+        if key == "rule_status" and self._snap is not None:
+            self._fill()
+        return dict.get(self, key, default)
+
+    def _all(name):
+        def method(self, *a, **k):
+            if self._snap is not None:
+                self._fill()
+            return getattr(dict, name)(self, *a, **k)
+        method.__name__ = name
+        return method
+
+    for _n in ("values", "items", "__eq__", "__ne__", "__repr__", "copy", "pop", "popitem", "setdefault", "__reduce_ex__",
+               "__reduce__", "__or__", "__ror__"):
+        locals()[_n] = _all(_n)
+    del _n, _all
+
+
+class _Details:
+    """What `info['rule_status']` is made of (SG.py:456-710, 901-950), as a function of the attributes below -- of the
+    env itself or of a per-step snapshot of them (`_Snap`)."""
+
+    def rule_status(self):
+        area, symbols, colors = self._region_symbols()
+        details = self._rule_details(area, symbols)
+        core = list(RULE_NAMES[:8])
+        status = {k: {"passed": self._flags[k], "detail": details[k]} for k in core}
+        status["all_rules_satisfied"] = {"passed": self._flags["all_rules_satisfied"],
+                                         "detail": {"rules_checked": core}}            # SG.py:931-935
+        status["_terminated"] = {"passed": True, "detail": False}              # SG.py:1011, 937-938 (Q16)
+        status["_truncated"] = {"passed": True, "detail": False}
+        status["_regions"] = {r: {"id": r, "area": area[r],                     # SG.py:949, 36-42
+                                  "symbol_counts": {k: len(v) for k, v in symbols[r].items()},
+                                  "colors": colors[r]} for r in range(len(area))}
+        return status
 
     def _region_symbols(self):
         """Per region id: area, symbols[layer] = [(x, y), ...] and colour counts (SG.py:456-482), from the
@@ -270,6 +265,125 @@ class SPaRC_Gym(_Env):
         nz = self.additional_info[self.additional_info != 0]
         return any(f"{v}" in self.polyshapes for v in nz)
 
+
+class _Snap(_Details):
+    """The state `rule_status` is a function of, frozen at one step: the static planes by reference (a puzzle load makes
+    fresh ones), the two dynamic planes and the device's verdicts by value."""
+
+    def __init__(self, env):
+        self.obs_array = dict(env.obs_array)
+        self.obs_array["visited"] = env.obs_array["visited"].copy()
+        self.obs_array["agent_location"] = env.obs_array["agent_location"].copy()
+        self.color_array, self.additional_info = env.color_array, env.additional_info
+        self._agent_location, self._target_location = env._agent_location.copy(), env._target_location
+        self.start_location, self.x_size, self.y_size = env.start_location, env.x_size, env.y_size
+        self.polyshapes, self._flags = env.polyshapes, env._flags
+        self._region_map, self._region_fit = env._region_map, env._region_fit
+
+
+class SPaRC_Gym(_Details, _Env):
+    metadata = {"render_modes": ["human", "llm"], "render_fps": 30}            # SG.py:45
+
+    def __init__(self, df_name="lkaesberg/SPaRC", df_split="all", df_set="test", render_mode=None,
+                 observation="new", traceback=False, max_steps=2000, *, puzzles=None, device="cuda:0"):
+        if observation not in ("new", "SPaRC"):
+            raise ValueError("Invalid observation type. Choose 'new' or 'SPaRC'.")     # SG.py:207
+        from .vec_env import SparcVecEnv
+        self.render_mode, self.observation = render_mode, observation
+        self.traceback, self.max_steps = traceback, max_steps
+        rows = puzzles if puzzles is not None else _load_rows(df_name, df_split, df_set)
+        if rows is None or len(rows) == 0:
+            raise ValueError("No valid dataframe provided")                    # SG.py:86-87
+        self.puzzles = ingest_rows(rows, observation)
+        self._store = PuzzleStore(self.puzzles)
+        # 'continue': a finished episode is stepped like a live one, as in the reference (Q4); every call validates
+        # the state it leaves behind (sparc_step_info_host), so the step itself need not
+        self._vec = SparcVecEnv(self._store, 1, traceback=traceback, max_steps=max_steps,
+                                autoreset_mode="continue", validate="never", device=device)
+        self._fast = hasattr(self._vec, "step_info_host")      # (the CPU twin used by the host-logic tests has no such call)
+        self._last_info = None
+        self.current_puzzle_index = 0
+        self.current_step = 0
+        self.rule_status = {}
+        self.action_space = _spaces.Discrete(4)                                # SG.py:210
+        self._load_puzzle(0)                                                   # SG.py:90
+
+    # -- device -> reference containers
+    def _load_puzzle(self, index):
+        import torch
+        pz = self.puzzles[index]
+        self._pz = pz
+        self.x_size, self.y_size = pz.X, pz.Y
+        self.difficulty, self.polyshapes = pz.difficulty, pz.polyshapes
+        self.solution_paths, self.solution_count = pz.solution_paths, pz.solution_count
+        self.start_location, self.target_location = pz.start, pz.target
+        self.normal_reward = 0
+        self.outcome_reward = 0
+        rec = self._vec.reset_info_host([index]) if self._fast else None
+        if rec is None:
+            self._vec.reset(puzzle_idx=torch.tensor([index], dtype=torch.int32))
+        # fresh containers per load, then updated in place while the episode runs (SG.py:149-151, 979)
+        self.obs_array = {k: np.zeros((pz.X, pz.Y), np.int32) for k in pz.keys}
+        self.color_array = np.zeros((pz.X, pz.Y), np.int32)
+        self.additional_info = np.zeros((pz.X, pz.Y), np.int64)
+        self._agent_location = np.zeros(2, np.int32)
+        self._target_location = np.array(pz.target, dtype=np.int32)
+        self._pull(rec, planes=True)
+        if self.observation == "SPaRC":                                        # SG.py:153-164, 198-204
+            self.observ = [[str(c) for c in row] for row in pz.observ]
+            if any(len(r) != len(self.observ[0]) for r in self.observ):
+                raise ValueError("Non-rectangular SPaRC grid")
+            init_json = self._build_json_obs()
+            self.observation_space = _spaces.Text(max_length=int(len(init_json) * 2),
+                                                  charset="".join(sorted(set(init_json) | set("LV."))))
+            return
+        keys = list(self.obs_array.keys())
+        self.observation_space = _spaces.Dict({                                # SG.py:190-196
+            "base": _spaces.Dict({k: _spaces.Box(low=0, high=1, shape=(pz.X, pz.Y), dtype=np.int32) for k in keys}),
+            "color": _spaces.Box(low=0, high=8, shape=(pz.X, pz.Y), dtype=np.int32),
+            "additional_info": _spaces.Box(low=0, high=143632, shape=(pz.X, pz.Y), dtype=np.int64)})
+
+    def _pull(self, rec=None, planes=False):
+        """The device results of the last reset / step -> the reference's containers.  rec: the host record of
+        sparc_*_info_host, or None = fetch field by field (the CPU twin of the tests).  planes: copy the observation
+        planes from the device (after a reset); a step touches them in place instead (`_move`)."""
+        v, st, pz = self._vec, self._store, self._pz
+        if rec is None:
+            flags, rmap, rfit = v.validate(region_map=True, region_fit=True)
+            rec = {"rule_flags": flags.cpu().numpy().view(np.uint16), "region_map": rmap.cpu().numpy(), "region_fit": rfit.cpu().numpy(),
+                   "agent_location": v.agent_xy.cpu().numpy(), "current_step": v.step_count.cpu().numpy(),
+                   "legal_mask": v.legal_mask.cpu().numpy(), "reward_code": v.reward_code.cpu().numpy(),
+                   "terminated": v.terminated.cpu().numpy(), "truncated": v.truncated.cpu().numpy()}
+            planes = True
+        if planes:
+            base = v.obs["base"][0].cpu().numpy()
+            for pi, key in enumerate(st.plane_keys):
+                if key in self.obs_array:
+                    self.obs_array[key][...] = base[pi, :pz.X, :pz.Y]
+            self.color_array[...] = v.obs["color"][0, :pz.X, :pz.Y].cpu().numpy()
+            self.additional_info[...] = v.obs["additional_info"][0, :pz.X, :pz.Y].cpu().numpy()
+        self._agent_location[...] = rec["agent_location"][0]
+        self.current_step = int(rec["current_step"][0])
+        lm = int(rec["legal_mask"][0])
+        self._legal = [a for a in range(4) if (lm >> a) & 1]
+        f = int(rec["rule_flags"][0]) & 0xFFFF
+        self._flags = {name: bool((f >> k) & 1) for k, name in enumerate(RULE_NAMES)}
+        self._region_map = rec["region_map"][0, :pz.X, :pz.Y].copy()
+        self._region_fit = rec["region_fit"][0].copy()
+        return rec
+
+    def _move(self, old, new):
+        """In-place update of the planes after the agent moved (SG.py:1141-1188): a node it had visited before means a
+        traceback undo (legality only allows path[-2], SG.py:1046-1048), which gives the left node back."""
+        vis, ag = self.obs_array["visited"], self.obs_array["agent_location"]
+        undo = vis[new] == 1
+        ag[old] = 0
+        if undo:
+            vis[old] = 0
+        vis[new] = 1
+        ag[new] = 1
+        return undo
+
     def _build_json_obs(self):                                                  # SG.py:988-992
         import json
         return json.dumps(self.observ, separators=(",", ":"))
@@ -280,23 +394,22 @@ class SPaRC_Gym(_Env):
         return {"base": self.obs_array, "color": self.color_array, "additional_info": self.additional_info}
 
     def _get_info(self):                                                        # SG.py:994-1022
-        area, symbols, colors = self._region_symbols()
-        details = self._rule_details(area, symbols)
-        core = list(RULE_NAMES[:8])
-        status = {k: {"passed": self._flags[k], "detail": details[k]} for k in core}
-        status["all_rules_satisfied"] = {"passed": self._flags["all_rules_satisfied"],
-                                         "detail": {"rules_checked": core}}            # SG.py:931-935
-        status["_terminated"] = {"passed": True, "detail": False}              # SG.py:1011, 937-938 (Q16)
-        status["_truncated"] = {"passed": True, "detail": False}
-        status["_regions"] = {r: {"id": r, "area": area[r],                     # SG.py:949, 36-42
-                                  "symbol_counts": {k: len(v) for k, v in symbols[r].items()},
-                                  "colors": colors[r]} for r in range(len(area))}
-        self.rule_status = status
-        return {"solution_count": self.solution_count, "difficulty": self.difficulty,
-                "grid_x_size": self.x_size, "grid_y_size": self.y_size,
-                "legal_actions": list(self._legal), "current_step": self.current_step,
-                "agent_location": self._agent_location, "rule_status": status,
-                "Rewards": {"normal_reward": self.normal_reward, "outcome_reward": self.outcome_reward}}
+        info = _LazyInfo({"solution_count": self.solution_count, "difficulty": self.difficulty,
+                          "grid_x_size": self.x_size, "grid_y_size": self.y_size,
+                          "legal_actions": list(self._legal), "current_step": self.current_step,
+                          "agent_location": self._agent_location, "rule_status": _LazyInfo._PENDING,
+                          "Rewards": {"normal_reward": self.normal_reward, "outcome_reward": self.outcome_reward}},
+                         _Snap(self))
+        self._last_info = info
+        return info
+
+    @property
+    def rule_status(self):                                                      # SG.py:64, 1010 (an attribute there)
+        return self._last_info["rule_status"] if self._last_info is not None else {}
+
+    @rule_status.setter
+    def rule_status(self, value):
+        pass
 
     # -- reference surface
     def reset(self, seed=None, options=None):                                   # SG.py:1057-1108
@@ -323,27 +436,62 @@ class SPaRC_Gym(_Env):
         except (TypeError, ValueError):
             a = -1                                                              # `action in legal` is False (SG.py:1137)
         v = self._vec
-        if int(v.terminated[0]) or int(v.truncated[0]):
-            raise RuntimeError("episode is over: call reset() (the B200 env does not step finished episodes, SURVEY Q4)")
         old = (int(self._agent_location[0]), int(self._agent_location[1]))
-        old_len = int(self.obs_array["visited"].sum())
-        v.step(torch.tensor([a], dtype=torch.int64))
-        code = int(v.reward_code[0])
-        terminated, truncated = bool(int(v.terminated[0])), bool(int(v.truncated[0]))
+        if self._fast:
+            rec = v.step_info_host([a])
+            self._pull(rec)
+        else:                                    # field-by-field fetch: the planes come from the device, already moved
+            old_len = int(self.obs_array["visited"].sum())
+            v.step(torch.tensor([a], dtype=torch.int64))
+            rec = self._pull(None)
+        code = int(rec["reward_code"][0])
+        terminated, truncated = bool(int(rec["terminated"][0])), bool(int(rec["truncated"][0]))
         self.normal_reward = abi.REWARD_VALUES[code]                            # ints 0/1/-1, floats +-0.01
-        self.outcome_reward = {3: 1, 4: -1}.get(code, 0)                        # SG.py:1204-1215
-        self._pull()
+        if code in (3, 4):                                                      # SG.py:1204-1215
+            self.outcome_reward = 1 if code == 3 else -1
+        elif not (terminated or truncated):
+            self.outcome_reward = 0          # (a final step with reward 0: past the end after a win, outcome stays 1)
         new = (int(self._agent_location[0]), int(self._agent_location[1]))
-        if self.observation == "SPaRC" and new != old:                          # text overlays, SG.py:1149-1184
-            if int(self.obs_array["visited"].sum()) < old_len:                  # traceback undo restores the node
-                self.observ[old[1]][old[0]] = "." if self.obs_array["gaps"][old] == 1 else "+"
-            else:
-                self.observ[old[1]][old[0]] = "V"
-            self.observ[new[1]][new[0]] = "L"
+        if new != old:
+            undo = self._move(old, new) if self._fast else int(self.obs_array["visited"].sum()) < old_len
+            if self.observation == "SPaRC":                                     # text overlays, SG.py:1149-1184
+                self.observ[old[1]][old[0]] = ("." if self.obs_array["gaps"][old] == 1 else "+") if undo else "V"
+                self.observ[new[1]][new[0]] = "L"
         return self._get_obs(), self.normal_reward, terminated, truncated, self._get_info()
 
     def render(self):                                                           # SG.py:1269-1299
-        return None
+        """The board as text, [y][x] like the reference's 'SPaRC' grid: 'L' agent, 'V' visited, 'E' target, 'G' gap,
+        '.' dot, symbols as <kind initial><count / shape id>-<colour id>, '+' free node.  'human': printed, returns None
+        (the reference opens a pygame window); 'llm': returned (the reference's docstring promises a text)."""
+        if self.render_mode not in ("human", "llm"):
+            return None
+        p, col, info = self.obs_array, self.color_array, self.additional_info
+        rows = []
+        for y in range(self.y_size):
+            cells = []
+            for x in range(self.x_size):
+                c = "+"
+                for key in p:
+                    if key not in FIXED_KEYS and key != "dot" and p[key][x, y] == 1:
+                        c = key[0].upper() + (str(int(info[x, y])) if info[x, y] else "") + (f"-{int(col[x, y])}" if col[x, y] else "")
+                if "dot" in p and p["dot"][x, y] == 1:
+                    c = "."
+                if p["gaps"][x, y] == 1 and x % 2 + y % 2 == 1:
+                    c = "G"
+                if p["target_location"][x, y] == 1:
+                    c = "E"
+                if p["visited"][x, y] == 1:
+                    c = "V"
+                if p["agent_location"][x, y] == 1:
+                    c = "L"
+                cells.append(c)
+            rows.append(cells)
+        wid = max(len(c) for r in rows for c in r)
+        text = "\n".join(" ".join(c.ljust(wid) for c in r).rstrip() for r in rows)
+        if self.render_mode == "human":
+            print(text)
+            return None
+        return text
 
     def close(self):
         if getattr(self, "_vec", None) is not None:

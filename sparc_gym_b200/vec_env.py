@@ -30,7 +30,9 @@ class DeviceStore:
         self.lib = abi.load_library()
         desc, keep = abi.store_desc(store)
         handle = C.c_void_p()
-        abi.check(self.lib.sparc_store_create(C.byref(desc), self.device.index or 0, C.byref(handle)))
+        index = self.device.index if self.device.index is not None else torch.cuda.current_device()   # bare 'cuda' = the current device
+        self.device = torch.device("cuda", index)
+        abi.check(self.lib.sparc_store_create(C.byref(desc), index, C.byref(handle)))
         self.handle = handle
 
     def close(self):
@@ -132,6 +134,10 @@ class SparcVecEnv:
         which envs to reset (None = all)."""
         idx_ptr = mask_ptr = None
         if puzzle_idx is not None:
+            if not (isinstance(puzzle_idx, torch.Tensor) and puzzle_idx.is_cuda):      # host data: range-check before uploading
+                chk = np.asarray(puzzle_idx)
+                if chk.size and (chk.min() < 0 or chk.max() >= self.store.n_puzzles):
+                    raise ValueError("puzzle index out of range")
             self._idx = torch.as_tensor(puzzle_idx, dtype=torch.int32, device=self.device).contiguous()
             idx_ptr = self._idx.data_ptr()
         if mask is not None:
@@ -166,6 +172,48 @@ class SparcVecEnv:
             abi.check(self.lib.sparc_step_host(self.handle, ptr(actions_host), ptr(reward_host), ptr(terminated_host),
                                                ptr(truncated_host),
                                                C.byref(self._obs_out if self.write_obs else self._no_obs), self._stream()))
+
+    # -- host-record calls (the single-env drop-in): one launch sequence, ONE device->host copy, no torch ops
+    def _info_record(self):
+        if getattr(self, "_rec", None) is None:
+            n, S = self.num_envs, self.store.slab_x * self.store.slab_y
+            nbytes = self.lib.sparc_info_record_bytes(self.handle)
+            self._rec_t = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+            self._ints_t = torch.zeros(n, dtype=torch.int32).pin_memory()
+            buf, self._ints = self._rec_t.numpy(), self._ints_t.numpy()
+            view = lambda off, cnt, dt, shape: buf[off:off + cnt * np.dtype(dt).itemsize].view(dt).reshape(shape)
+            self._rec = {"current_step": view(0, n, np.int32, (n,)), "rule_flags": view(4 * n, n, np.uint16, (n,)),
+                         "agent_location": view(6 * n, 2 * n, np.uint8, (n, 2)), "reward_code": view(8 * n, n, np.int8, (n,)),
+                         "terminated": view(9 * n, n, np.uint8, (n,)), "truncated": view(10 * n, n, np.uint8, (n,)),
+                         "legal_mask": view(11 * n, n, np.uint8, (n,)),
+                         "region_fit": view(12 * n, abi.MAX_REGIONS * n, np.int8, (n, abi.MAX_REGIONS)),
+                         "region_map": view((12 + abi.MAX_REGIONS) * n, S * n, np.int8, (n, self.store.slab_x, self.store.slab_y))}
+        return self._rec
+
+    def step_info_host(self, actions):
+        """sparc_step_info_host: step every env with the int32 `actions` (host), validate the resulting states and return
+        the host record (numpy views of one pinned buffer, overwritten by the next call): current_step, rule_flags,
+        agent_location, reward_code, terminated, truncated, legal_mask, region_fit, region_map."""
+        rec = self._info_record()
+        self._ints[...] = actions
+        abi.check(self.lib.sparc_step_info_host(self.handle, self._ints_t.data_ptr(), self._rec_t.data_ptr(),
+                                                C.byref(self._obs_out if self.write_obs else self._no_obs), self._stream()))
+        return rec
+
+    def reset_info_host(self, puzzle_idx=None):
+        """sparc_reset_info_host: clean reset of every env (on `puzzle_idx`, int32 host array, or its current puzzle) and
+        the same host record as step_info_host."""
+        rec = self._info_record()
+        ptr = None
+        if puzzle_idx is not None:
+            idx = np.asarray(puzzle_idx)
+            if idx.min() < 0 or idx.max() >= self.store.n_puzzles:
+                raise ValueError("puzzle index out of range")
+            self._ints[...] = idx
+            ptr = self._ints_t.data_ptr()
+        abi.check(self.lib.sparc_reset_info_host(self.handle, ptr, self._rec_t.data_ptr(),
+                                                 C.byref(self._obs_out if self.write_obs else self._no_obs), self._stream()))
+        return rec
 
     def encode(self):
         """Rewrite the observation tensors from the current state without stepping (sparc_encode)."""
@@ -262,15 +310,25 @@ class SparcVectorEnv(SparcVecEnv):
         self.plane_keys = list(st.plane_keys)
 
     def reset(self, *, seed=None, options=None, mask=None):
-        idx = None
-        if options:
+        """The reference's cursor rules (SG.py:1075-1087), per env: `options` given -> the env whose `puzzle_id` is in
+        the pool goes there, an unknown id keeps the env's current puzzle, the seed is ignored; else a seed draws the
+        indices; else every env advances its cursor by one (cyclically).  The cursors live on the host and follow
+        explicit resets only (autoresets move the device-side puzzle by `puzzle_stride` on their own)."""
+        n = self.store.n_puzzles
+        if getattr(self, "_cursor", None) is None:
+            self._cursor = np.arange(self.num_envs, dtype=np.int64) % n
+        sel = np.ones(self.num_envs, bool) if mask is None else np.asarray(torch.as_tensor(mask).cpu()).astype(bool)
+        cur = self._cursor.copy()
+        if options is not None:
             if "puzzle_index" in options:
-                idx = options["puzzle_index"]
+                cur = np.asarray(torch.as_tensor(options["puzzle_index"]).cpu()).astype(np.int64)
             elif "puzzle_id" in options:
                 ids = options["puzzle_id"]
                 ids = [ids] * self.num_envs if isinstance(ids, str) else list(ids)
-                cur = torch.arange(self.num_envs) % self.store.n_puzzles
-                idx = torch.tensor([self.store.id_to_index.get(i, int(c)) for i, c in zip(ids, cur)], dtype=torch.int32)
+                cur = np.array([self.store.id_to_index.get(i, int(c)) for i, c in zip(ids, cur)], dtype=np.int64)
         elif seed is not None:
-            idx = torch.from_numpy(np.random.default_rng(seed).integers(self.store.n_puzzles, size=self.num_envs).astype(np.int32))
-        return super().reset(puzzle_idx=idx, mask=mask)
+            cur = np.random.default_rng(seed).integers(n, size=self.num_envs).astype(np.int64)
+        else:
+            cur = (cur + 1) % n
+        self._cursor = np.where(sel, cur, self._cursor)
+        return super().reset(puzzle_idx=torch.from_numpy(self._cursor.astype(np.int32)), mask=mask)

@@ -271,7 +271,32 @@ def make_sparc_text():
     dump("sparc_text.json.gz", {"rows": rows, "episodes": episodes})
 
 
+def make_postdone():
+    """the reference has no guard after done -- step() keeps moving the agent and keeps returning +-1.
+    Episodes stepped 12 actions PAST their end (stop_at_done=False), both traceback modes, small max_steps so that
+    truncation by step count happens too; the drop-in (autoreset mode CONTINUE) must reproduce every output."""
+    rows = golden_rows()[40:]
+    episodes = []
+    for tb in (False, True):
+        ref = rh.make_reference_env(rows, observation="new", traceback=tb, max_steps=14)
+        for i, row in enumerate(rows):
+            from fuzzrows import solution_actions
+            planted = row["id"].startswith("syn")
+            for ep in range(2):
+                rng = np.random.default_rng([i, ep, int(tb), 77])
+                if planted and ep == 0:
+                    acts = solution_actions(row, 0)[:13] + [int(a) for a in rng.integers(0, 4, 12)]
+                else:
+                    acts = fuzz_actions(row, 17 * i + ep + 500 * tb, 26)
+                trace = run_episode(ref, row["id"], acts, pre_reset=rh.zero_leak, stop_at_done=False)
+                episodes.append({"row": i, "traceback": tb, "max_steps": 14, "actions": acts, "trace": trace})
+    dump("postdone.json.gz", {"rows": rows, "episodes": episodes})
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "postdone":      # (added in round 2; the other files are unchanged)
+        make_postdone()
+        sys.exit(0)
     if not rh.reference_available():
         sys.exit("reference not present; golden vectors can only be regenerated in the build container")
     make_sparc_text()
@@ -280,3 +305,4 @@ if __name__ == "__main__":
     make_polyfit()
     make_traces()
     make_config1()
+    make_postdone()

@@ -144,6 +144,41 @@ def test_stats_reduction_over_gloo_world_size_2():
     assert dict(out[0]) == want and dict(out[1]) == want
 
 
+def _gloo_async_worker(rank, world, port, out):
+    import torch
+    import torch.distributed as dist
+    from sparc_gym_b200.runner import AsyncStats
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    counters = torch.zeros(8, dtype=torch.int64)
+    a = AsyncStats(lambda stream: counters, every=4)
+    seen = []
+    for t in range(1, 21):
+        counters += torch.arange(8, dtype=torch.int64) * (rank + 1)          # this rank's "step"
+        a.tick()
+        if t % 4 == 0:
+            # an all-reduce on the DEFAULT group in between: the statistics travel on a communicator of their own
+            x = torch.ones(1)
+            dist.all_reduce(x)
+    got = a.latest(wait=True)
+    seen.append(got)
+    out[rank] = (a.reductions, got[0], got[1])
+    dist.destroy_process_group()
+
+
+def test_async_stats_reduction_over_gloo_world_size_2():
+    """AsyncStats (ShardedRunner.stats_async): periodic reduction over a process group of its own, every 4th tick; the
+    newest completed result is the sum over ranks of the counters at tick 20."""
+    import torch.multiprocessing as mp
+    mgr = mp.Manager()
+    out = mgr.dict()
+    port = 30600 + os.getpid() % 1000
+    mp.spawn(_gloo_async_worker, args=(2, port, out), nprocs=2, join=True)
+    want = {n: k * 20 * 3 for k, n in enumerate(abi.STAT_NAMES)}            # ranks add k and 2k per tick
+    for r in (0, 1):
+        n_red, tick, stats = out[r]
+        assert n_red == 5 and tick == 20 and stats == want
+
+
 def test_rows_survive_a_parquet_round_trip(tmp_path):
     """Real SPaRC rows arrive as pandas/pyarrow objects (numpy arrays of dicts, numpy scalars): the
     loader + ingest must give the same planes as the plain-Python rows."""

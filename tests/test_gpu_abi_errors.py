@@ -69,8 +69,9 @@ def test_python_surface_raises_like_the_reference():
     for a in (0, 1, 2):
         _, _, te, tr, _ = env.step(a)
     assert te or tr                                                               # max_steps = 3
-    with pytest.raises(RuntimeError, match="episode is over"):                    # finished episodes are not stepped
-        env.step(0)
+    _, r, te, tr, info = env.step(0)                  # like the reference, a finished episode is stepped on
+    assert tr and r in (1, -1) and type(r) is int and info["current_step"] == 4
+    assert sparc_gym_b200.SPaRC_Gym(puzzles=rows, render_mode="human").render_mode == "human"      # accepted, SG.py:68-74
     from sparc_gym_b200.vec_env import SparcVecEnv
     with pytest.raises(KeyError):
         SparcVecEnv(rows, 4, obs_format="float16")

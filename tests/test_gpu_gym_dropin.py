@@ -79,3 +79,42 @@ def test_dropin_config1_rollout_matches_reference():
     env = sparc_gym_b200.make("SPaRc-Gym", puzzles=[g["row"]], observation="new", traceback=False,
                               max_steps=g["config"]["max_steps"])
     assert replay_config1(env, g) == g["golden"]["episodes"] > 100
+
+
+def test_dropin_steps_past_the_end_like_the_reference():
+    """the reference does not guard a finished episode; its recorded outputs for 12 steps past done
+    (tests/golden/postdone.json.gz), incl. the sticky outcome reward after a win."""
+    import sparc_gym_b200
+    with gzip.open(os.path.join(G, "postdone.json.gz"), "rb") as f:
+        g = json.loads(f.read())
+    envs, steps = {}, 0
+    for ep in g["episodes"]:
+        key = (ep["traceback"], ep["max_steps"])
+        if key not in envs:
+            envs[key] = sparc_gym_b200.make("SPaRC-Gym", puzzles=g["rows"], observation="new", traceback=key[0], max_steps=key[1])
+        row = g["rows"][ep["row"]]
+        got = run_episode(envs[key], row["id"], ep["actions"], stop_at_done=False)
+        d = diff_traces(ep["trace"], json.loads(json.dumps(got)))
+        assert d is None, f"{row['id']} traceback={key[0]}: {d}"
+        steps += len(got)
+    assert steps > 1800
+
+
+def test_dropin_info_is_lazy_but_belongs_to_its_step_and_render_is_text():
+    import sparc_gym_b200
+    from fuzzrows import solution_actions
+    from sparc_gym_b200.dataset import RULES_FULL, gen_puzzle
+    row = gen_puzzle(5, 5, 3, RULES_FULL)
+    env = sparc_gym_b200.make("SPaRc-Gym", puzzles=[row], render_mode="llm", max_steps=80)
+    obs, info = env.reset(options={"puzzle_id": row["id"]})
+    infos = [info]
+    for a in solution_actions(row, 0):
+        obs, r, te, tr, info = env.step(a)
+        infos.append(info)
+    assert te and r == 1 and type(r) is int
+    assert infos[0]["rule_status"]["reached_target"]["passed"] is False            # filled in only now
+    assert infos[-1]["rule_status"]["all_rules_satisfied"]["passed"] is True
+    mid = infos[len(infos) // 2]
+    assert mid["rule_status"]["reached_target"]["detail"]["agent_loc"] != infos[-1]["rule_status"]["reached_target"]["detail"]["agent_loc"]
+    text = env.render()
+    assert isinstance(text, str) and text.count("\n") == env.y_size - 1 and "L" in text and "V" in text

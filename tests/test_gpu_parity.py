@@ -142,9 +142,16 @@ def test_step_host_matches_device_step():
         r = torch.empty(n, dtype=torch.float32).pin_memory()
         te = torch.empty(n, dtype=torch.uint8).pin_memory()
         tr = torch.empty(n, dtype=torch.uint8).pin_memory()
+        keep = torch.empty(n, dtype=torch.uint8).pin_memory()
         for t in range(30):
             act = torch.from_numpy(rng.integers(0, 4, n).astype(np.uint8))
-            a.step_host(act.pin_memory(), r, te, tr)
+            if t < 10:
+                a.step_host(act.pin_memory(), r, te, tr)       # a new host buffer every call (small batches: a new graph each time)
+            elif t < 25:
+                keep.copy_(act)
+                a.step_host(keep, r, te, tr)                   # the same buffers: the captured graph is replayed
+            else:
+                a.step_host(act.numpy(), r, te, tr)            # pageable memory: the plain call sequence
             ob, rb, tb, ub, _ = b.step(act.cuda())
             assert torch.equal(r, rb.cpu()) and torch.equal(te, tb.cpu()) and torch.equal(tr, ub.cpu()), (n, t)
             assert all(torch.equal(a.obs[k], ob[k]) for k in ob)
@@ -191,6 +198,16 @@ def test_vector_env_face_reset_options():
     assert env.single_observation_space is not None and env.num_envs == 12 and env.plane_keys[:4] == ["visited", "gaps", "agent_location", "target_location"]
     out = env.step(torch.zeros(12, dtype=torch.int64, device="cuda"))
     assert len(out) == 5 and out[1].shape == (12,)
+    # the reference's cursor rules (SG.py:1075-1087), per env: no seed / no options advances the cursor by one,
+    # an unknown puzzle_id keeps the env's current puzzle, a seed is ignored when options are given
+    env.reset(options={"puzzle_index": torch.arange(12, dtype=torch.int32) % 6})
+    obs, _ = env.reset()
+    o2, _ = solo.reset(options={"puzzle_index": (torch.arange(12, dtype=torch.int32) + 1) % 6})
+    assert all(torch.equal(obs[k], o2[k]) for k in obs)
+    obs, _ = env.reset(seed=5, options={"puzzle_id": "no-such-puzzle"})
+    assert all(torch.equal(obs[k], o2[k]) for k in obs)
+    with pytest.raises(ValueError):
+        env.reset(options={"puzzle_index": np.array([0] * 11 + [6], dtype=np.int32)})
 
 
 def test_dense_polyomino_boards_on_the_gpu(monkeypatch):

@@ -36,3 +36,22 @@ def test_verify_paths_against_oracle():
         assert bool(res["terminated"][k]) == te and bool(res["truncated"][k]) == tr, k
         for name in so.RULE_NAMES:
             assert bool(res[name][k]) == info["rule_status"][name]["passed"], (k, name)
+
+
+def test_all_rows_sweep_over_dataset_files(tmp_path):
+    """tools/verify_dataset.py on JSON / JSONL / parquet copies of a pool in the dataset's schema: the refused row is
+    reported, every listed solution of the generated rows earns +1 on the GPU (CPU twin: tests/test_dropin_host_logic.py)."""
+    import importlib.util
+    import os
+    from sparc_gym_b200.dataset import load_rows
+    from test_dropin_host_logic import _dataset_files
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("verify_dataset", os.path.join(root, "tools", "verify_dataset.py"))
+    vd = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(vd)
+    rows, paths = _dataset_files(tmp_path)
+    for ext, p in paths.items():
+        rep = vd.sweep(load_rows(p), device="cuda:0")
+        assert rep["accepted"] == len(rows) and [r["id"] for r in rep["rejected"]] == ["too-wide"], ext
+        assert rep["solutions_rewarded_plus_one"] >= 20 and rep["solutions_satisfying_all_rules"] >= 10
+        assert all(f["id"].startswith("fuzz") for f in rep["reward_failures"])

@@ -37,6 +37,23 @@ def test_traces_match_reference():
     assert len(wins) >= 8
 
 
+def test_stepping_past_the_end_matches_reference():
+    """no guard after done -- the reference's own outputs for up to 12 steps past the end of an episode."""
+    g = load("postdone.json.gz")
+    envs, post = {}, 0
+    for ep in g["episodes"]:
+        key = (ep["traceback"], ep["max_steps"])
+        if key not in envs:
+            envs[key] = so.OracleEnv(g["rows"], observation="new", traceback=key[0], max_steps=key[1])
+        row = g["rows"][ep["row"]]
+        got = run_episode(envs[key], row["id"], ep["actions"], stop_at_done=False)
+        d = diff_traces(ep["trace"], json.loads(json.dumps(got)))
+        assert d is None, f"{row['id']} traceback={key[0]}: {d}"
+        done = [s["terminated"] or s["truncated"] for s in ep["trace"][1:]]
+        post += sum(done[1:][i] is not None for i in range(len(done) - 1) if any(done[:i + 1]))
+    assert post > 900
+
+
 def test_polyfit_known_answers():
     cases = load("polyfit.json.gz")
     assert sum(c["expected"] for c in cases) > 50 and sum(not c["expected"] for c in cases) > 50
