@@ -36,7 +36,9 @@ extern "C" {
 #define SPARC_BOARD_WORDS     8      /* 256-bit node boards */
 #define SPARC_MAX_PLANES     10      /* visited,gaps,agent_location,target_location + 6 symbol kinds */
 #define SPARC_MAX_SHAPES     32      /* distinct polyshapes referenced by one puzzle */
-#define SPARC_MAX_YLOPS       6      /* ylop instances in one puzzle (3-bit demand counters) */
+#define SPARC_MAX_YLOPS       6      /* ylop instances in one puzzle served by the 4-bit demand counters of the fast search */
+#define SPARC_MAX_YLOPS_WIDE 30      /* ... by the 6-bit counters (header flag bit 2); the reference has no limit, but its search
+                                        enumerates 49^k ylop anchors (SG.py:794-816) */
 #define SPARC_MAX_REGIONS    64      /* region ids per env (one per rule cell at most: 7 x 7 = 49) */
 /* poly/ylop verdict of one region (SG.py:674-702) */
 enum { SPARC_FIT_NONE = 0,           /* no poly / ylop instance in the region */
@@ -91,7 +93,8 @@ typedef struct {                 /* 32 bytes */
     uint8_t  target_x, target_y; /* SG.py:268 */
     uint8_t  n_shapes;           /* shape slots of this puzzle */
     uint8_t  flags;              /* bit0: solution_count > 0; bit1: has stars / squares / shape instances
-                                    (a region rule can fail, so the validator must segment regions) */
+                                    (a region rule can fail, so the validator must segment regions);
+                                    bit2: more than SPARC_MAX_YLOPS ylop instances (wide demand counters) */
     uint32_t shape_off;          /* index of the first SparcShape */
     uint32_t trie_root;          /* trie node of the start location, 0 = no listed solution starts there */
     int32_t  solution_count;

@@ -600,12 +600,57 @@ SPARC_HD int fit_step(FitState& f, const SparcShape* shapes, int ns, int code, i
     }
 }
 
+// signed 6-bit bit-sliced per-cell counters (-32..31) for puzzles with more than six ylop instances
+struct Cnt6 { uint64_t b[6]; };
+struct NarrowCnt {
+    typedef Cnt4 C;
+    enum { max_ylops = SPARC_MAX_YLOPS };
+    static SPARC_HD C make(uint64_t region) { C c = {region, 0, 0, 0}; return c; }
+    static SPARC_HD void add(C& c, uint64_t m) { cnt4_add(c, m); }
+    static SPARC_HD void sub(C& c, uint64_t m) { cnt4_sub(c, m); }
+    static SPARC_HD int get(const C& c, int bit) { return cnt4_get(c, bit); }
+    static SPARC_HD uint64_t eq(const C& c, int k) { return cnt4_eq(c, k); }
+    static SPARC_HD uint64_t positive(const C& c) { return (c.b0 | c.b1 | c.b2) & ~c.b3; }
+    static SPARC_HD uint64_t nonzero(const C& c) { return c.b0 | c.b1 | c.b2 | c.b3; }
+};
+struct WideCnt {
+    typedef Cnt6 C;
+    enum { max_ylops = SPARC_MAX_YLOPS_WIDE };
+    static SPARC_HD C make(uint64_t region) { C c = {{region, 0, 0, 0, 0, 0}}; return c; }
+    static SPARC_HD void add(C& c, uint64_t m) {
+#pragma unroll
+        for (int i = 0; i < 6; i++) { const uint64_t t = c.b[i] & m; c.b[i] ^= m; m = t; }
+    }
+    static SPARC_HD void sub(C& c, uint64_t m) {
+#pragma unroll
+        for (int i = 0; i < 6; i++) { const uint64_t t = ~c.b[i] & m; c.b[i] ^= m; m = t; }
+    }
+    static SPARC_HD int get(const C& c, int bit) {
+        int v = 0;
+#pragma unroll
+        for (int i = 0; i < 5; i++) v += (int)((c.b[i] >> bit) & 1) << i;
+        return v - 32 * (int)((c.b[5] >> bit) & 1);
+    }
+    static SPARC_HD uint64_t eq(const C& c, int k) {
+        uint64_t r = ~0ull;
+#pragma unroll
+        for (int i = 0; i < 6; i++) r &= ~(c.b[i] ^ (((k >> i) & 1) ? ~0ull : 0ull));
+        return r;
+    }
+    static SPARC_HD uint64_t positive(const C& c) { return (c.b[0] | c.b[1] | c.b[2] | c.b[3] | c.b[4]) & ~c.b[5]; }
+    static SPARC_HD uint64_t nonzero(const C& c) { return c.b[0] | c.b[1] | c.b[2] | c.b[3] | c.b[4] | c.b[5]; }
+};
+
 // The plain depth-first search with its whole state in registers (no ordinal / split bookkeeping): what one thread runs
 // for one region in the fused kernel, in k_val and in sparc_validate.  Same tree, same order as fit_init + fit_step with
 // nsplit = 0 (tests/test_exact_fit.py counts the nodes of both).  1 = fits, 0 = does not, -1 = `budget` nodes spent
 // (budget <= 0: unlimited).
-SPARC_HD int exact_fit_budget(uint64_t region, int w, int h, const SparcShape* shapes, int ns,
-                              const Cnt8& n_poly, const Cnt8& n_ylop, int budget) {
+// CW = the per-cell demand counters: NarrowCnt (4 bit planes: up to SPARC_MAX_YLOPS = 6 ylop instances, every pool
+// the generator or the tests build) or WideCnt (6 bit planes: up to SPARC_MAX_YLOPS_WIDE = 30, puzzles whose header
+// carries flag bit 2 -- the reference has no limit, but its own search enumerates 49^k ylop anchors).
+template <class CW>
+SPARC_HD int exact_fit_budget_t(uint64_t region, int w, int h, const SparcShape* shapes, int ns,
+                                const Cnt8& n_poly, const Cnt8& n_ylop, int budget) {
     SPARC_COUNT_FIT_CALL();
     Cnt8 rem_p = n_poly, rem_y = n_ylop;
     uint8_t fr_cell[128], fr_q[128];                          // DFS edges: q < 2ns placement, 0xFF = advance
@@ -625,8 +670,8 @@ SPARC_HD int exact_fit_budget(uint64_t region, int w, int h, const SparcShape* s
         if (ny) have_y |= 1u << s;
         if ((sh.mask & SPARC_CELLS56) == 1ull) mono_slots |= 1u << s;
     }
-    if (tot_y > SPARC_MAX_YLOPS) return 0;                // (ingest guarantees this never happens)
-    Cnt4 c = {region, 0, 0, 0};
+    if (tot_y > CW::max_ylops) return 0;                  // (ingest guarantees this never happens)
+    typename CW::C c = CW::make(region);
     uint64_t grid = 0;
     for (int cx = 0; cx < w; cx++) grid |= ((1ull << h) - 1ull) << (cx * 8);
     int level = 0, cell = 0, q = 0;
@@ -634,9 +679,9 @@ SPARC_HD int exact_fit_budget(uint64_t region, int w, int h, const SparcShape* s
     for (int it = 0;; it++) {
         if (budget > 0 && it >= budget) return -1;
         SPARC_COUNT_FIT();
-        const int n = cnt4_get(c, cell);
+        const int n = CW::get(c, cell);
         const uint64_t later = grid & ~((2ull << cell) - 1ull);               // cells after `cell`
-        const uint64_t floor_cells = cnt4_eq(c, -tot_y) & later;              // later cells already at what ylops can lift
+        const uint64_t floor_cells = CW::eq(c, -tot_y) & later;              // later cells already at what ylops can lift
         bool found = false;
         if (q < ns && n + 1 <= tot_p) {                                       // anchor a ylop here (slots >= q)
             for (uint32_t cand = have_y & (0xFFFFFFFFu << q); cand; cand &= cand - 1) {
@@ -644,7 +689,7 @@ SPARC_HD int exact_fit_budget(uint64_t region, int w, int h, const SparcShape* s
                 const uint64_t m = shape_at(load_shape(shapes + s), cell);
                 if (!m) continue;
                 if (floor_cells & ~m) continue;               // one ylop fewer can lift later cells: those at the floor would be lost
-                cnt4_add(c, m); cnt8_add(rem_y, s, -1); tot_y--;
+                CW::add(c, m); cnt8_add(rem_y, s, -1); tot_y--;
                 if (!cnt8_get(rem_y, s)) have_y &= ~(1u << s);
                 fr_cell[level] = (uint8_t)cell; fr_q[level] = (uint8_t)s; level++;
                 q = s; found = true;
@@ -658,14 +703,14 @@ SPARC_HD int exact_fit_budget(uint64_t region, int w, int h, const SparcShape* s
                 const uint64_t m = shape_at(load_shape(shapes + s), cell);
                 if (!m) continue;
                 if (floor_cells & m) continue;                // would sink below what ylops can lift
-                cnt4_sub(c, m); cnt8_add(rem_p, s, -1); tot_p--;
+                CW::sub(c, m); cnt8_add(rem_p, s, -1); tot_p--;
                 if (tot_y == 0 && all_connected) {
-                    const uint64_t D = (c.b0 | c.b1 | c.b2) & ~c.b3;          // cells still demanded
+                    const uint64_t D = CW::positive(c);                        // cells still demanded
                     const uint64_t iso = D & ~((D << 1) | (D >> 1) | (D << 8) | (D >> 8));
                     if (iso) {
                         int monos = 0;
                         for (uint32_t ms = mono_slots; ms; ms &= ms - 1) monos += cnt8_get(rem_p, sp_ffs(ms) - 1);
-                        if (sp_popcll(iso) > monos) { cnt4_add(c, m); cnt8_add(rem_p, s, 1); tot_p++; continue; }
+                        if (sp_popcll(iso) > monos) { CW::add(c, m); cnt8_add(rem_p, s, 1); tot_p++; continue; }
                     }
                 }
                 if (!cnt8_get(rem_p, s)) have_p &= ~(1u << s);
@@ -676,7 +721,7 @@ SPARC_HD int exact_fit_budget(uint64_t region, int w, int h, const SparcShape* s
         }
         if (found) continue;
         if (n == 0) {                                                         // settled: advance
-            const uint64_t open = (c.b0 | c.b1 | c.b2 | c.b3) & later;        // later cells with non-zero demand
+            const uint64_t open = CW::nonzero(c) & later;                      // later cells with non-zero demand
             if (tot_p + tot_y == 0) { if (!open) return 1; }               // nothing left and nothing demanded
             else if (later && (tot_y > 0 || open)) {
                 // with ylops still to place every later cell is a candidate anchor; without, only a
@@ -692,12 +737,18 @@ SPARC_HD int exact_fit_budget(uint64_t region, int w, int h, const SparcShape* s
             cell = fr_cell[level];
             const int qq = fr_q[level];
             if (qq == 0xFF) continue;                                         // advance was the last child
-            if (qq < ns) { cnt4_sub(c, shape_at(load_shape(shapes + qq), cell)); cnt8_add(rem_y, qq, 1); tot_y++; have_y |= 1u << qq; }
-            else { cnt4_add(c, shape_at(load_shape(shapes + qq - ns), cell)); cnt8_add(rem_p, qq - ns, 1); tot_p++; have_p |= 1u << (qq - ns); }
+            if (qq < ns) { CW::sub(c, shape_at(load_shape(shapes + qq), cell)); cnt8_add(rem_y, qq, 1); tot_y++; have_y |= 1u << qq; }
+            else { CW::add(c, shape_at(load_shape(shapes + qq - ns), cell)); cnt8_add(rem_p, qq - ns, 1); tot_p++; have_p |= 1u << (qq - ns); }
             q = qq + 1;
             break;
         }
     }
+}
+
+SPARC_HD int exact_fit_budget(uint64_t region, int w, int h, const SparcShape* shapes, int ns,
+                              const Cnt8& n_poly, const Cnt8& n_ylop, int budget, bool wide = false) {
+    if (wide) return exact_fit_budget_t<WideCnt>(region, w, h, shapes, ns, n_poly, n_ylop, 0);
+    return exact_fit_budget_t<NarrowCnt>(region, w, h, shapes, ns, n_poly, n_ylop, budget);
 }
 
 // one copy of the search: `code` / `nsplit` select its share of the tree (0, 0 = all of it)
@@ -867,7 +918,7 @@ SPARC_HD int validate_env(const StoreDev& st, uint32_t puzzle, const uint32_t* v
                 VP_TIC();
                 if (net != sp_popcll(R)) verdict = SPARC_FIT_AREA_MISMATCH;   // SG.py:679-682
                 else {
-                    const int fit = exact_fit_budget(R, w, hh, shapes, h.n_shapes, np, nyl, fit_budget);
+                    const int fit = exact_fit_budget(R, w, hh, shapes, h.n_shapes, np, nyl, fit_budget, (h.flags & 4) != 0);
                     if (fit < 0) return -1;
                     if (!fit) verdict = SPARC_FIT_NO_TILING;
                 }

@@ -288,7 +288,16 @@ __device__ __forceinline__ int validate_warp(const StoreDev& st, uint32_t qw, in
                     const int net = __reduce_add_sync(VW_FULL, (pa - yb) * (int)(sh_anchors >> 56));
                     if (net != __popcll(Rj)) { poly_ok = false; continue; }    // SG.py:679-682
                     vp_tmp = VW_CLOCK();
-                    if (!HARD) {
+                    if (hflags & 4) {              // more than six ylop instances: the plain search on 6-bit counters, every lane alike
+                        Cnt8 np = {{0, 0, 0, 0}}, nyl = {{0, 0, 0, 0}};
+                        for (unsigned mm = __ballot_sync(VW_FULL, (pa | yb) != 0); mm; mm &= mm - 1) {
+                            const int sl = __ffs((int)mm) - 1;
+                            cnt8_add(np, sl, __shfl_sync(VW_FULL, pa, sl)); cnt8_add(nyl, sl, __shfl_sync(VW_FULL, yb, sl));
+                        }
+                        const int fit = exact_fit_budget(Rj, w, hh, shapes, n_shapes, np, nyl, 0, true);
+                        if (HARD) { const unsigned long long bit = 1ull << (nsearch & 63); nsearch++; if (fit) fmask |= bit; }
+                        else if (!fit) poly_ok = false;
+                    } else if (!HARD) {
                         const int fit = exact_fit_coop(Rj, w, hh, shapes, n_shapes, pa, yb, lane, stack, budget);
                         if (fit < 0) return -1;                                // a hard board: the snapshot becomes a hard item
                         if (!fit) poly_ok = false;

@@ -374,6 +374,38 @@ def gen_dense_poly_puzzle(w, h, seed, puzzle_id=None):
     return row
 
 
+def gen_many_ylops_puzzle(seed, solvable=True, puzzle_id=None):
+    """A 3x3 board that is ONE region (the listed solution runs along the border) holding a full 3x3 poly, a second poly
+    of seven cells and SEVEN one-cell ylops: more ylop instances than the fast exact-fit search's 4-bit counters serve
+    (store flag bit 2 -> 6-bit counters).  It tiles: the ylops sit exactly under the second poly.  `solvable=False`
+    gives the second poly an eighth cell, so the areas no longer balance (9 + 8 - 7 != 9) and the rule fails."""
+    rng = np.random.default_rng([int(seed), 0x7109])
+    full = [[1, 1, 1], [1, 1, 1], [1, 1, 1]]
+    holes = [(0, 0), (0, 2), (2, 0), (2, 2)]
+    hx, hy = holes[int(rng.integers(len(holes)))]
+    second = [[0 if (i, j) == (hx, hy) else 1 for j in range(3)] for i in range(3)]          # 8 cells
+    if solvable:
+        second[1][1] = 0                                                                     # 7 cells (still 4-connected)
+    ylops = [[[1]]] * 7
+    shapes = {"31": full, "32": second, "33": [[1]], "34": [[1, 1]]}
+    cells, k = [], 0
+    inst = [("poly", 31), ("poly", 32)] + [("ylop", 33 if y == [[1]] else 34) for y in ylops]
+    for kind, sid in inst:
+        cx, cy = divmod(k, 3)
+        k += 1
+        cells.append({"position": {"x": 2 * cx + 1, "y": 2 * cy + 1},
+                      "properties": {"type": kind, "color": COLOR_NAMES[k % 8], "polyshape": sid}})
+    w = h = 3
+    path = [(0, y) for y in range(2 * h, -1, -1)] + [(x, 0) for x in range(1, 2 * w + 1)]
+    text = {"puzzle": {"start": {"x": 0, "y": 2 * h}, "end": {"x": 2 * w, "y": 0}, "cells": cells}}
+    row = {"id": puzzle_id or f"ylops-{int(seed):04d}-{'ok' if solvable else 'no'}", "difficulty_level": 5,
+           "grid_size": {"width": w, "height": h}, "solution_count": 1,
+           "solutions": [{"path": [{"x": x, "y": y} for x, y in path]}],
+           "polyshapes": json.dumps(shapes), "text_visualization": json.dumps(text)}
+    row["puzzle_array"] = puzzle_array(row, text)
+    return row
+
+
 def gen_pool(n, sizes, rules, seed0=0, **kw):
     """`n` rows; sizes is a list of (w, h) cycled over; row i uses seed seed0+i."""
     return [gen_puzzle(*sizes[i % len(sizes)], seed0 + i, rules, **kw) for i in range(n)]

@@ -24,7 +24,8 @@ from .ingest import FIXED_KEYS, SYMBOL_KEYS, Puzzle
 MAX_DIM = 15
 BOARD_WORDS = 8
 MAX_SHAPES = 32
-MAX_YLOPS = 6
+MAX_YLOPS = 6            # served by the 4-bit demand counters of the fast exact-fit search
+MAX_YLOPS_WIDE = 30      # ... by the 6-bit counters (header flag bit 2)
 TRIE_NODE_WORDS = 8
 PLANE_IDS = {k: i for i, k in enumerate(FIXED_KEYS + SYMBOL_KEYS)}
 DIRS = ((1, 0), (0, -1), (-1, 0), (0, 1))   # action id -> (dx, dy)  (SG.py:212-217)
@@ -293,8 +294,11 @@ class PuzzleStore:
                         n_ylops += 1
             if len(slots) > MAX_SHAPES:
                 raise ValueError(f"puzzle {pz.id}: more than {MAX_SHAPES} distinct polyshapes")
+            if n_ylops > MAX_YLOPS_WIDE:
+                raise ValueError(f"puzzle {pz.id}: more than {MAX_YLOPS_WIDE} ylop instances (the reference accepts them, but "
+                                 "its exact-fit search enumerates 49^k anchor combinations, SG.py:794-816)")
             if n_ylops > MAX_YLOPS:
-                raise ValueError(f"puzzle {pz.id}: more than {MAX_YLOPS} ylop instances")
+                hdr["flags"] |= 4           # wide demand counters in the exact-fit search
             hdr["n_shapes"] = len(slots)
             if slots or cb[CB_STAR] or cb[CB_SQUARE]:
                 hdr["flags"] |= 2           # some region rule (squares / stars / shapes) can fail

@@ -123,13 +123,14 @@ int emu_validate(const SparcStoreDesc* desc, uint32_t* core, uint32_t* vis, int3
     return 0;
 }
 
-// direct access to the two exact-fit searches (which: 0 = sweep used by the kernels, 1 = reference order)
+// direct access to the exact-fit searches (which: 0 = sweep used by the kernels, 1 = reference order, 2 = sweep on wide counters)
 int emu_exact_fit(int which, uint64_t region, int w, int h, const SparcShape* shapes, int ns,
                   const uint8_t* n_poly, const uint8_t* n_ylop, long long* iters) {
     g_fit_iters = 0;
     Cnt8 np = {{0, 0, 0, 0}}, ny = {{0, 0, 0, 0}};
     for (int s = 0; s < ns; s++) { cnt8_add(np, s, n_poly[s]); cnt8_add(ny, s, n_ylop[s]); }
-    const bool ok = which ? exact_fit_reference_order(region, w, h, shapes, ns, n_poly, n_ylop)
+    const bool ok = which == 2 ? exact_fit_budget(region, w, h, shapes, ns, np, ny, 0, true) != 0      // 6-bit demand counters
+                  : which ? exact_fit_reference_order(region, w, h, shapes, ns, n_poly, n_ylop)
                           : exact_fit(region, w, h, shapes, ns, np, ny);
     if (iters) *iters = g_fit_iters;
     return ok ? 1 : 0;

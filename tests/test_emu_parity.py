@@ -192,3 +192,27 @@ def test_delta_observation_equals_full_rewrite(fmt, mode, traceback, defer):
         assert np.array_equal(ra[1], rb[1]) and np.array_equal(ra[2], rb[2]) and np.array_equal(ra[3], rb[3])
         assert np.array_equal(ra[4]["rule_flags"], rb[4]["rule_flags"]) and np.array_equal(ra[4]["legal_mask"], rb[4]["legal_mask"])
     assert np.array_equal(a.stats(), b.stats()) and (mode == "disabled" or a.stats()[0] > N)
+
+
+def test_more_than_six_ylops_run_on_wide_counters():
+    """A puzzle with seven ylop instances is accepted (the reference has no limit), flagged for the 6-bit demand counters
+    and validated: the tiling variant passes every rule on its listed solution, the variant whose areas do not balance
+    fails the poly rule only (independent answers for such boards: tests/test_exact_fit.py)."""
+    from fuzzrows import solution_actions
+    from sparc_gym_b200.dataset import gen_many_ylops_puzzle
+    from sparc_gym_b200.ingest import ingest_rows
+    from sparc_gym_b200.store import PuzzleStore
+    rows = [gen_many_ylops_puzzle(s, solvable=(s % 2 == 0)) for s in range(8)] + gen_pool(4, [(3, 3)], RULES_FULL, seed0=3)
+    st = PuzzleStore(ingest_rows(rows))
+    assert [int(f) & 4 for f in st.headers["flags"]] == [4] * 8 + [0] * 4
+    for defer in (False, True):
+        env = EmuVecEnv(rows, len(rows), max_steps=100, autoreset_mode="disabled", validate="terminal", defer_validation=defer)
+        env.reset()
+        sols = [solution_actions(r, 0) for r in rows]
+        flags = np.zeros(len(rows), np.uint16)
+        for t in range(max(map(len, sols))):
+            a = np.array([s[t] if t < len(s) else 4 for s in sols], np.uint8)
+            _, r, te, tr, info = env.step(a)
+            flags = np.where(info["rule_flags"] != 0, info["rule_flags"], flags)
+        assert [hex(int(f)) for f in flags[:8]] == ["0x81ff", "0x807f"] * 4, [hex(int(f)) for f in flags]
+        assert all(int(f) == 0x81ff for f in flags[8:])

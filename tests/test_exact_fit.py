@@ -72,7 +72,7 @@ def test_golden_polyfit_cases():
     assert n > 100
 
 
-def random_case(rng):
+def random_case(rng, max_ylops=6):
     w, h = int(rng.integers(1, 6)), int(rng.integers(1, 6))
     need = np.zeros((w, h), int)
     polys, ylops = [], []
@@ -124,7 +124,7 @@ def random_case(rng):
             polys[int(rng.integers(len(polys)))] = shapes[int(rng.integers(len(shapes)))]
         else:
             polys.append(shapes[int(rng.integers(3))])
-    return 2 * w + 1, 2 * h + 1, region, polys, ylops[:6]
+    return 2 * w + 1, 2 * h + 1, region, polys, ylops[:max_ylops]
 
 
 def test_sweep_equals_reference_order_and_oracle():
@@ -233,3 +233,104 @@ def test_split_search_on_dense_boards():
             warp_nodes = min(r[1] for r in res if r[0]) if want else max(r[1] for r in res)
             ratios.append(warp_nodes / it_plain)
     assert ratios and float(np.median(ratios)) < 0.5, ratios
+
+
+def brute_fit(X, Y, region, polys, ylops):
+    """Independent exhaustive answer for small boards: every multiset of ylop anchors (instances of one shape in
+    non-decreasing anchor order), then an exact cover of the resulting demand by the polys (translation only, anchored at
+    the shape's first cell in (x, y) order -- SG.py:856-871)."""
+    w, h = (X - 1) // 2, (Y - 1) // 2
+
+    def cells_at(a, cx, cy):
+        a = np.array(a)
+        pts = [(i, j) for i in range(a.shape[0]) for j in range(a.shape[1]) if a[i, j]]
+        if not pts:
+            return None
+        ai, aj = pts[0]
+        out = [(cx + i - ai, cy + j - aj) for i, j in pts]
+        return out if all(0 <= x < w and 0 <= y < h for x, y in out) else None
+
+    need0 = np.zeros((w, h), int)
+    for (x, y) in region:
+        need0[x // 2, y // 2] = 1
+    polys = [p for p in polys if np.array(p).sum() > 0]
+    ylops = sorted((json.dumps(y) for y in ylops if np.array(y).sum() > 0))
+
+    def cover(need, left):
+        if (need < 0).any():
+            return False
+        if not left:
+            return not need.any()
+        nz = np.argwhere(need > 0)
+        if len(nz) == 0:
+            return False
+        cx, cy = map(int, nz[0])
+        tried = set()
+        for k, p in enumerate(left):
+            key = json.dumps(p)
+            if key in tried:
+                continue
+            tried.add(key)
+            c = cells_at(p, cx, cy)
+            if c is None:
+                continue
+            n2 = need.copy()
+            for x, y in c:
+                n2[x, y] -= 1
+            if cover(n2, left[:k] + left[k + 1:]):
+                return True
+        return False
+
+    def place(k, need, last):
+        if k == len(ylops):
+            return cover(need, polys)
+        shape = json.loads(ylops[k])
+        start = last if k and ylops[k] == ylops[k - 1] else 0
+        for a in range(start, w * h):
+            c = cells_at(shape, a // h, a % h)
+            if c is None:
+                continue
+            n2 = need.copy()
+            for x, y in c:
+                n2[x, y] += 1
+            if place(k + 1, n2, a):
+                return True
+        return False
+
+    return place(0, need0, 0)
+
+
+def test_wide_counters_agree_with_the_fast_search_and_with_brute_force():
+    """Puzzles with more than six ylop instances run the same sweep on 6-bit demand counters (header flag bit 2): on cases
+    the 4-bit search can do it gives the same answers node for node, and with 7-12 ylops it agrees with an independent
+    exhaustive search on small boards."""
+    rng = np.random.default_rng(21)
+    n = 0
+    while n < 300:
+        X, Y, region, polys, ylops = random_case(rng)
+        if not region or not polys or sum(map(area, polys)) - sum(map(area, ylops)) != len(region):
+            continue
+        a, ia = device_fit(0, X, Y, region, polys, ylops)
+        b, ib = device_fit(2, X, Y, region, polys, ylops)
+        assert a == b and ia == ib, (X, Y, region, polys, ylops)
+        n += 1
+    n = n_fit = n_many = 0
+    while n < 60:
+        X, Y, region, polys, ylops = random_case(rng, max_ylops=12)
+        w, h = (X - 1) // 2, (Y - 1) // 2
+        if w * h > 9 or len(ylops) < 7 or not region or not polys:
+            continue
+        # rebalance with monominoes so that the areas match and the search actually runs
+        gap = sum(map(area, polys)) - sum(map(area, ylops)) - len(region)
+        if gap > 0:
+            ylops = ylops + [[[1]]] * gap
+        elif gap < 0:
+            polys = polys + [[[1]]] * (-gap)
+        if len(ylops) > 12:
+            continue
+        got, _ = device_fit(2, X, Y, region, polys, ylops)
+        assert got == brute_fit(X, Y, region, polys, ylops), (X, Y, region, polys, ylops)
+        n += 1
+        n_fit += got
+        n_many += len(ylops) > 6
+    assert n_many == 60 and 5 < n_fit < 60

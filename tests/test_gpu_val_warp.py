@@ -76,3 +76,29 @@ def test_dense_polyomino_boards():
         gen_pool(16, [(6, 6)], RULES_FULL, seed0=9000)
     judged, wins, passes = _run(rows, 8192, 30, False, 100, seed=3, follow=0.9)
     assert judged > 5000 and wins > 5000 and 0 < passes < judged      # some dense boards tile, most do not
+
+
+def test_more_than_six_ylops():
+    """Puzzles with seven ylop instances (6-bit demand counters, header flag bit 2) through the split step's k_val, the
+    delta step's k_post and sparc_validate: listed solutions give 0x81ff / 0x807f (areas balanced / not)."""
+    from sparc_gym_b200.dataset import gen_many_ylops_puzzle
+    from sparc_gym_b200.vec_env import SparcVecEnv
+    rows = [gen_many_ylops_puzzle(s, solvable=(s % 2 == 0)) for s in range(16)] + gen_pool(16, [(3, 3), (4, 4)], RULES_FULL, seed0=77)
+    N = 8192 + 32
+    sols = [solution_actions(r, 0) for r in rows]
+    T = max(map(len, sols))
+    table = np.full((len(rows), T), 4, np.uint8)
+    for i, s in enumerate(sols):
+        table[i, :len(s)] = s
+    pz = np.arange(N) % len(rows)
+    for upd in ("rewrite", "delta"):
+        env = SparcVecEnv(rows, N, max_steps=200, autoreset_mode="disabled", validate="terminal", obs_update=upd)
+        env.reset()
+        flags = torch.zeros(N, dtype=torch.int32, device="cuda")
+        for t in range(T):
+            _, _, te, tr, info = env.step(torch.from_numpy(np.ascontiguousarray(table[pz, t])).cuda())
+            f = info["rule_flags"].to(torch.int32) & 0xFFFF
+            flags = torch.where(f != 0, f, flags)
+        want = np.where(pz < 16, np.where(pz % 2 == 0, 0x81FF, 0x807F), 0x81FF)
+        assert np.array_equal(flags.cpu().numpy(), want), upd
+        assert np.array_equal((env.validate().to(torch.int32) & 0xFFFF).cpu().numpy(), want)
