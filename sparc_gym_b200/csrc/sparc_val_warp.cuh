@@ -34,7 +34,9 @@ __device__ __forceinline__ uint64_t vw_u64(uint32_t lo, uint32_t hi) { return ((
 // One share of a HARD search (k_val): the whole warp runs copy `code` of the split search converged -- every lane
 // the same fit_step (sparc_core.cuh) -- while the other copies run in other warps, anywhere on the chip.  `found` /
 // `bit`: the item's found mask; a copy gives up as soon as another copy has found a fit for this region.
-#define VW_HARD_NSPLIT 6
+#ifndef VW_HARD_NSPLIT
+#define VW_HARD_NSPLIT 5            /* 32 shares: measured p99 of the dense-board tail 3.0 / 2.0 / 1.7 / 2.0 / 2.9 / 4.6 ms with 8 / 16 / 32 / 64 / 128 / 256 shares */
+#endif
 #define VW_HARD_CODES (1 << VW_HARD_NSPLIT)
 __device__ __noinline__ bool exact_fit_code(uint64_t region, int w, int h, const SparcShape* shapes, int ns,
                                             const Cnt8& n_poly, const Cnt8& n_ylop, int code,
