@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(CTA_THREADS) k_val(const KParams p) {
 
 // Each hard item is validated again by VW_HARD_CODES shares, share c searching part c of every search tree
 // (validate_warp<true> -> fit_step with code = c, the whole warp converged).  Shares are handed out through one
-// counter, so the 64 shares of a snapshot run wherever a warp is free.  A share that finds a fit sets the region's bit
+// counter, so the 32 shares of a snapshot run wherever a warp is free.  A share that finds a fit sets the region's bit
 // in the item's found mask (and thereby stops its siblings); the last share of a snapshot to finish writes its flags.
 // One warp per CTA: beside k_encode a 128-thread CTA of this kernel would need the registers of three retiring encoder CTAs.
 #define HARD_CTAS 1184

@@ -13,7 +13,7 @@
 //   * regions are flooded FOUR at a time (the four 8-lane groups start from seeds spread over the unlabelled cells);
 //   * the exact polyomino fit is a converged-warp depth-first search with one shape slot per lane (exact_fit_coop: every
 //     candidate placement of a node tested at once, two ballots pick the child); a search that outgrows its node budget
-//     sends the snapshot to the hard queue, where any free warp of k_val takes one of 64 shares of the search tree (fit_step with
+//     sends the snapshot to the hard queue, where k_val_hard runs VW_HARD_CODES shares of the search tree, one per warp (fit_step with
 //     code = share, sparc_core.cuh) and the last share to finish combines the verdicts.
 #pragma once
 #include "sparc_core.cuh"
