@@ -77,3 +77,27 @@ def test_python_surface_raises_like_the_reference():
         SparcVecEnv(rows, 4, obs_format="float16")
     with pytest.raises(KeyError):
         SparcVecEnv(rows, 4, autoreset_mode="sometimes")
+
+
+def test_nvtx_ranges_do_not_change_results():
+    """SPARC_NVTX=1 wraps every ABI call in an NVTX range (tracing); a fresh process, because the
+    switch is read once."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys; sys.path.insert(0, %r); import torch\n"
+            "from sparc_gym_b200.dataset import RULES_FULL, gen_pool\n"
+            "from sparc_gym_b200.vec_env import SparcVecEnv\n"
+            "rows = gen_pool(4, [(3, 3)], RULES_FULL, seed0=2)\n"
+            "out = []\n"
+            "for n in (64, 9000):\n"
+            "    env = SparcVecEnv(rows, n, max_steps=9, autoreset_mode='same_step'); env.reset()\n"
+            "    g = torch.Generator(device='cuda').manual_seed(1)\n"
+            "    for t in range(20): env.step(torch.randint(0, 4, (n,), dtype=torch.uint8, device='cuda', generator=g))\n"
+            "    out.append(env.stats().cpu().tolist())\n"
+            "print(out)\n") % root
+    runs = [subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300,
+                           env=dict(os.environ, SPARC_NVTX=v)) for v in ("0", "1")]
+    assert all(r.returncode == 0 for r in runs), runs[1].stderr[-400:]
+    assert runs[0].stdout == runs[1].stdout and "[[" in runs[0].stdout

@@ -24,10 +24,11 @@ def _policy_table(rows, T, rng):
     return table
 
 
-def _run(rows, N, T, traceback, max_steps, seed, follow):
+def _run(rows, N, T, traceback, max_steps, seed, follow, obs_update="rewrite"):
     from sparc_gym_b200.vec_env import SparcVecEnv
     rng = np.random.default_rng(seed)
-    env = SparcVecEnv(rows, N, traceback=traceback, max_steps=max_steps, autoreset_mode="disabled", validate="terminal")
+    env = SparcVecEnv(rows, N, traceback=traceback, max_steps=max_steps, autoreset_mode="disabled", validate="terminal",
+                      obs_update=obs_update)
     assert N >= 8192                                         # the split step: k_dyn -> k_val || k_encode
     table = _policy_table(rows, T, rng)
     pz = np.arange(N) % len(rows)
@@ -58,23 +59,27 @@ def _run(rows, N, T, traceback, max_steps, seed, follow):
     return judged, wins, passes
 
 
-def test_fuzzed_rows():
+@pytest.mark.parametrize("obs_update", ["rewrite", "delta"])
+def test_fuzzed_rows(obs_update):
     rows = [fuzz_row(s) for s in range(700, 820)]
-    judged, wins, passes = _run(rows, 8192 + 77, 48, True, 40, seed=1, follow=0.5)
+    judged, wins, passes = _run(rows, 8192 + 77, 48, True, 40, seed=1, follow=0.5, obs_update=obs_update)
     assert judged > 6000 and passes > 50
 
 
-@pytest.mark.parametrize("traceback", [False, True])
-def test_generated_full_rule_boards(traceback):
+@pytest.mark.parametrize("traceback,obs_update", [(False, "rewrite"), (True, "rewrite"), (True, "delta")])
+def test_generated_full_rule_boards(traceback, obs_update):
     rows = gen_pool(96, [(1, 1), (2, 3), (3, 3), (4, 4), (5, 5), (6, 6), (7, 7), (6, 3)], RULES_FULL, seed0=4000, extra_solutions=1)
-    judged, wins, passes = _run(rows, 16384, 150, traceback, 140, seed=2, follow=0.6)
+    judged, wins, passes = _run(rows, 16384, 150, traceback, 140, seed=2, follow=0.6, obs_update=obs_update)
     assert judged > 12000 and wins > 5000 and passes > 5000
 
 
-def test_dense_polyomino_boards():
+@pytest.mark.parametrize("obs_update", ["rewrite", "delta"])
+def test_dense_polyomino_boards(obs_update):
+    """(a pool with dense boards switches the node budgets and k_val_hard on: the thread-per-snapshot k_val of the
+    full-rewrite step and the warp-per-snapshot k_post of the delta step both hand their over-budget snapshots over)"""
     rows = [gen_dense_poly_puzzle(6, 6, s) for s in range(40)] + [gen_dense_poly_puzzle(5, 4, s) for s in range(8)] + \
         gen_pool(16, [(6, 6)], RULES_FULL, seed0=9000)
-    judged, wins, passes = _run(rows, 8192, 30, False, 100, seed=3, follow=0.9)
+    judged, wins, passes = _run(rows, 8192, 30, False, 100, seed=3, follow=0.9, obs_update=obs_update)
     assert judged > 5000 and wins > 5000 and 0 < passes < judged      # some dense boards tile, most do not
 
 
