@@ -17,9 +17,9 @@ device's dynamics.
 
 One step = ONE call into the library (sparc_step_info_host: action in, dynamics, validation of the new state, one
 packed record out); the numpy planes are touched in place where the agent moved (as SG.py:1146-1188 does) instead
-of being copied from the device, and `info['rule_status']` -- nine `detail` payloads and the region summaries,
-the bulk of the reference's own step time -- is a lazy mapping filled in from a snapshot of that step when it is
-first looked at.
+of being copied from the device.  `info` is the reference's plain dict; with the opt-in `lazy_info=True` its
+`rule_status` -- nine `detail` payloads and the region summaries, more Python time than the rest of the step -- is
+filled in from a snapshot of that step when it is first looked up (`_LazyInfo`).
 
 Deliberate differences from the reference:
 * resets are clean (SURVEY Q1: the reference leaks `visited` / `agent_location` across episodes of one puzzle);
@@ -77,43 +77,51 @@ def _load_rows(df_name, df_split, df_set):
 
 
 class _LazyInfo(dict):
-    """`info` of one step.  'rule_status' is computed from the step's snapshot the first time anything but the cheap
-    keys is looked at (the nine `detail` payloads and the region summaries cost more Python time than the rest of the
-    step); afterwards this is a plain dict with the reference's key order (SG.py:1012-1021)."""
-    __slots__ = ("_snap",)
+    """`info` of one step with `lazy_info=True` (an opt-in of this implementation, not the reference's behaviour):
+    'rule_status' is computed from the step's snapshot the first time it is looked up -- the nine `detail` payloads and
+    the region summaries cost more Python time than the rest of the step.  Lookups (`info['rule_status']`, `.get`,
+    `.items()`, `.values()`, `==`, `repr`, `copy`, pickling) fill it in; C-level copies of a dict subclass
+    (`dict(info)`, `{**info}`) read the storage directly and would see the placeholder -- call `info.materialise()`
+    first, or leave `lazy_info` off: the default `info` is the reference's plain dict."""
     _PENDING = object()
 
     def __init__(self, items, snap):
         super().__init__(items)
         self._snap = snap
 
-    def _fill(self):
+    def materialise(self):
         snap, self._snap = self._snap, None
         if snap is not None:
             dict.__setitem__(self, "rule_status", snap.rule_status())
+        return self
 
     def __getitem__(self, key):
         if key == "rule_status" and self._snap is not None:
-            self._fill()
+            self.materialise()
         return dict.__getitem__(self, key)
 
     def get(self, key, default=None):
         if key == "rule_status" and self._snap is not None:
-            self._fill()
+            self.materialise()
         return dict.get(self, key, default)
 
     def _all(name):
         def method(self, *a, **k):
             if self._snap is not None:
-                self._fill()
+                self.materialise()
             return getattr(dict, name)(self, *a, **k)
         method.__name__ = name
         return method
 
-    for _n in ("values", "items", "__eq__", "__ne__", "__repr__", "copy", "pop", "popitem", "setdefault", "__reduce_ex__",
-               "__reduce__", "__or__", "__ror__"):
+    for _n in ("values", "items", "__eq__", "__ne__", "__repr__", "pop", "popitem", "setdefault", "__or__", "__ror__"):
         locals()[_n] = _all(_n)
     del _n, _all
+
+    def copy(self):
+        return dict(self.materialise().items())
+
+    def __reduce_ex__(self, protocol):
+        return (dict, (dict(self.materialise().items()),))
 
 
 class _Details:
@@ -285,11 +293,11 @@ class SPaRC_Gym(_Details, _Env):
     metadata = {"render_modes": ["human", "llm"], "render_fps": 30}            # SG.py:45
 
     def __init__(self, df_name="lkaesberg/SPaRC", df_split="all", df_set="test", render_mode=None,
-                 observation="new", traceback=False, max_steps=2000, *, puzzles=None, device="cuda:0"):
+                 observation="new", traceback=False, max_steps=2000, *, puzzles=None, device="cuda:0", lazy_info=False):
         if observation not in ("new", "SPaRC"):
             raise ValueError("Invalid observation type. Choose 'new' or 'SPaRC'.")     # SG.py:207
         from .vec_env import SparcVecEnv
-        self.render_mode, self.observation = render_mode, observation
+        self.render_mode, self.observation, self.lazy_info = render_mode, observation, bool(lazy_info)
         self.traceback, self.max_steps = traceback, max_steps
         rows = puzzles if puzzles is not None else _load_rows(df_name, df_split, df_set)
         if rows is None or len(rows) == 0:
@@ -394,12 +402,16 @@ class SPaRC_Gym(_Details, _Env):
         return {"base": self.obs_array, "color": self.color_array, "additional_info": self.additional_info}
 
     def _get_info(self):                                                        # SG.py:994-1022
-        info = _LazyInfo({"solution_count": self.solution_count, "difficulty": self.difficulty,
-                          "grid_x_size": self.x_size, "grid_y_size": self.y_size,
-                          "legal_actions": list(self._legal), "current_step": self.current_step,
-                          "agent_location": self._agent_location, "rule_status": _LazyInfo._PENDING,
-                          "Rewards": {"normal_reward": self.normal_reward, "outcome_reward": self.outcome_reward}},
-                         _Snap(self))
+        items = {"solution_count": self.solution_count, "difficulty": self.difficulty,
+                 "grid_x_size": self.x_size, "grid_y_size": self.y_size,
+                 "legal_actions": list(self._legal), "current_step": self.current_step,
+                 "agent_location": self._agent_location, "rule_status": _LazyInfo._PENDING,
+                 "Rewards": {"normal_reward": self.normal_reward, "outcome_reward": self.outcome_reward}}
+        if self.lazy_info:
+            info = _LazyInfo(items, _Snap(self))
+        else:                                   # the reference's plain dict, everything computed now
+            info = items
+            info["rule_status"] = _Details.rule_status(self)
         self._last_info = info
         return info
 
