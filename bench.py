@@ -232,15 +232,17 @@ def cpu_baseline(workload, budget_s=10.0, samples=1, warmup=0, kind=None, cores=
     return out
 
 
-def dropin_bench(n_steps=10000, warmup=500, touch_info=False, device="cuda:0"):
+def dropin_bench(n_steps=10000, warmup=500, lazy_info=False, device="cuda:0"):
     """BASELINE configs[0] through the reference's own call surface: gym.make('SPaRc-Gym', observation='new',
     traceback=False, max_steps=1000) -> reset / step(action) with a Python int in and (obs dict of numpy planes, reward,
-    terminated, truncated, info) out, one env, every step a full round trip to the GPU.  touch_info: also read
-    info['rule_status'] every step (the lazy part of the drop-in's info)."""
+    terminated, truncated, info) out, one env, every step a full round trip to the GPU.  Default: `info` is the
+    reference's plain dict, rule_status built every step; lazy_info=True is the drop-in's opt-in (rule_status filled in
+    on first lookup, never looked up here)."""
     import sparc_gym_b200
     from sparc_gym_b200.dataset import config_pool
     row = config_pool(1)[0]
-    env = sparc_gym_b200.make("SPaRc-Gym", puzzles=[row], observation="new", traceback=False, max_steps=1000, device=device)
+    env = sparc_gym_b200.make("SPaRc-Gym", puzzles=[row], observation="new", traceback=False, max_steps=1000, device=device,
+                              lazy_info=lazy_info)
     acts = np.random.default_rng(0).integers(0, 4, n_steps + warmup).tolist()
     env.reset(options={"puzzle_id": row["id"]})
     episodes, t0 = 0, 0.0
@@ -248,15 +250,13 @@ def dropin_bench(n_steps=10000, warmup=500, touch_info=False, device="cuda:0"):
         if t == warmup:
             t0 = time.perf_counter()
         obs, r, te, tr, info = env.step(a)
-        if touch_info:
-            info["rule_status"]
         if te or tr:
             episodes += 1
             env.reset(options={"puzzle_id": row["id"]})
     dt = time.perf_counter() - t0
     env.close()
     return {"value": round(n_steps / dt, 1), "unit": "env-steps/s", "us_per_step": round(1e6 * dt / n_steps, 2), "steps": n_steps,
-            "episodes": episodes, "rule_status_read_every_step": touch_info}
+            "episodes": episodes, "lazy_info": lazy_info}
 
 
 def workload_config(args, world, store=None):
@@ -352,13 +352,13 @@ def main():
         if rank != 0:
             return
         assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
-        fast, eager = dropin_bench(touch_info=False), dropin_bench(touch_info=True)
+        fast, lazy = dropin_bench(lazy_info=False), dropin_bench(lazy_info=True)
         line = {"metric": "env-steps/sec (whole box)", "value": fast["value"], "unit": "env-steps/s", "n_gpus": 1,
                 "steps": fast["steps"], "warmup": 500, "ms_per_step": round(fast["us_per_step"] / 1e3, 5), "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
                 "config": {"workload": "config1", "description": WORKLOADS["config1"][5], "traceback": False, "max_steps": 1000,
                            "api": "sparc_gym_b200.make('SPaRc-Gym', ...).step(a): one env, host in / host out, wall clock"},
-                "dropin": fast, "dropin_rule_status_read": eager}
+                "dropin": fast, "dropin_lazy_info": lazy}
         if not args.no_cpu_baseline:
             res = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", "config1",
                                   "--steps", "2", "--warmup", "1", "--cpu-seconds", "4", "--no-extra"], capture_output=True, text=True)

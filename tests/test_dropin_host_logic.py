@@ -86,15 +86,17 @@ def test_dropin_steps_past_the_end_like_the_reference(dropin):
         assert d is None, f"{row['id']} traceback={key[0]}: {d}"
 
 
-def test_dropin_lazy_info_and_text_render(dropin, capsys):
-    """`info` behaves like the reference's plain dict (key order, equality, json) although rule_status is filled in on
-    first use -- from a snapshot of ITS step, not of the env's current state; render_mode is accepted as in the
-    reference and render() draws text."""
+@pytest.mark.parametrize("lazy", [False, True])
+def test_dropin_lazy_info_and_text_render(dropin, capsys, lazy):
+    """`info` is the reference's plain dict by default; with lazy_info=True it behaves like one (key order, equality,
+    json) although rule_status is filled in on first use -- from a snapshot of ITS step, not of the env's current
+    state; render_mode is accepted as in the reference and render() draws text."""
     from sparc_gym_b200.dataset import RULES_FULL, gen_puzzle
     from fuzzrows import solution_actions
     row = gen_puzzle(4, 4, 2, RULES_FULL)
-    env = dropin.make("SPaRc-Gym", puzzles=[row], render_mode="llm", max_steps=50)
+    env = dropin.make("SPaRc-Gym", puzzles=[row], render_mode="llm", max_steps=50, lazy_info=lazy)
     obs, info0 = env.reset(options={"puzzle_id": row["id"]})
+    assert (type(info0) is dict) == (not lazy)
     assert list(info0.keys()) == ["solution_count", "difficulty", "grid_x_size", "grid_y_size", "legal_actions", "current_step",
                                   "agent_location", "rule_status", "Rewards"]
     infos = [info0]

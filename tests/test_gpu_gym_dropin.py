@@ -100,12 +100,13 @@ def test_dropin_steps_past_the_end_like_the_reference():
     assert steps > 1800
 
 
-def test_dropin_info_is_lazy_but_belongs_to_its_step_and_render_is_text():
+@pytest.mark.parametrize("lazy", [False, True])
+def test_dropin_info_is_lazy_but_belongs_to_its_step_and_render_is_text(lazy):
     import sparc_gym_b200
     from fuzzrows import solution_actions
     from sparc_gym_b200.dataset import RULES_FULL, gen_puzzle
     row = gen_puzzle(5, 5, 3, RULES_FULL)
-    env = sparc_gym_b200.make("SPaRc-Gym", puzzles=[row], render_mode="llm", max_steps=80)
+    env = sparc_gym_b200.make("SPaRc-Gym", puzzles=[row], render_mode="llm", max_steps=80, lazy_info=lazy)
     obs, info = env.reset(options={"puzzle_id": row["id"]})
     infos = [info]
     for a in solution_actions(row, 0):
