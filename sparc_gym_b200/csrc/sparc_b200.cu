@@ -121,6 +121,27 @@ __device__ __forceinline__ void reduce_stats(const KParams& p, bool have, const 
     }
 }
 
+// -DENV_PROFILE (tools/envprof.py): where one CTA of the fused k_env spends its time.  Thread 0 of every CTA reads
+// clock64 after phase A (its own env), after the barrier behind it (= the CTA's slowest env), after stages 1a / 1b and at
+// the end of the CTA (behind one more barrier), plus globaltimer at both ends.  g_envprof: 0 CTAs, 1-5 sums of the five
+// marks in cycles since the CTA began, 6-10 their maxima, 11 / 12 earliest begin / latest end (ns), 13 sum of begins (low
+// 32 bits, ns).  Not compiled otherwise.
+#if defined(ENV_PROFILE)
+__device__ unsigned long long g_envprof[16];
+__device__ __forceinline__ unsigned long long ep_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define EP_BEGIN() const unsigned long long ep_g0 = ep_ns(); const long long ep_t0 = clock64(); long long ep_m[4] = {0, 0, 0, 0}
+#define EP_MARK(k) (ep_m[k] = clock64() - ep_t0)
+#define EP_END() do { __syncthreads(); if (threadIdx.x == 0) { const unsigned long long ep_e = (unsigned long long)(clock64() - ep_t0); \
+    atomicAdd(&g_envprof[0], 1ull); \
+    for (int k = 0; k < 4; k++) { atomicAdd(&g_envprof[1 + k], (unsigned long long)ep_m[k]); atomicMax(&g_envprof[6 + k], (unsigned long long)ep_m[k]); } \
+    atomicAdd(&g_envprof[5], ep_e); atomicMax(&g_envprof[10], ep_e); \
+    atomicMin(&g_envprof[11], ep_g0); atomicMax(&g_envprof[12], ep_ns()); atomicAdd(&g_envprof[13], ep_g0 & 0xffffffffull); } } while (0)
+#else
+#define EP_BEGIN() ((void)0)
+#define EP_MARK(k) ((void)0)
+#define EP_END() ((void)0)
+#endif
+
 // ---- simple kernel: one CTA = one tile (small batches: every CTA is resident at once) ----------
 template <int FMT>
 __global__ void __launch_bounds__(CTA_THREADS, SPARC_MINBLOCKS) k_env(const KParams p) {
@@ -132,29 +153,55 @@ __global__ void __launch_bounds__(CTA_THREADS, SPARC_MINBLOCKS) k_env(const KPar
     uint32_t* head = smem;
     uint32_t* flats = smem + tile_head_words(p.tile);
 
+    uint32_t* tflags = flats + tile_flat_words(st, p.tile);      // [tile] PA_* of every env | [tile][SPARC_VQ_WORDS] snapshots
+    uint32_t* snaps = tflags + p.tile;
+    EP_BEGIN();
     EnvRegs e;
     unsigned long long my_stats[SPARC_N_STATS];
     bool have_stats = false;
-    bool full = false;
+    // (The warps that wait for phase A prefetching the static rows of the env's puzzle and of its same-step successor
+    // into L1 -- prefetch.global.L1 -- made the steady-state step slower, 8.30 -> 8.80 us on config 2: between graph
+    // replays those few KB stay cached anyway.)
     if (tid < nE) {
-        have_stats = phase_a(p, env0 + tid, e, head + tid * SPARC_DYN_STRIDE, my_stats, &full);
+        // a state that needs validating is left in shared memory: warp 3 validates it while warps 0-2 encode (inline,
+        // the other 127 threads of the CTA waited at the barrier for it: 10.1 -> 8.8 us per step on config 2)
+        int fl = 0;
+        have_stats = phase_a<false, true>(p, env0 + tid, e, head + tid * SPARC_DYN_STRIDE, my_stats, &fl, snaps + tid * SPARC_VQ_WORDS);
+        tflags[tid] = (uint32_t)fl;
         head[p.tile * SPARC_DYN_STRIDE + tid] = e.puzzle;
         write_dyn(st, head, tid, e);
     }
+    EP_MARK(0);
     if (p.mode == 0 && tid < ((nE + 31) & ~31)) reduce_stats(p, have_stats, my_stats);
-    if (!p.obs.base_dev && !p.obs.color_dev && !p.obs.info_dev) return;
-    if (p.mode == 0 && p.obs.update == SPARC_OBS_DELTA) {
-        // persistent observation: phase A has touched the cells that changed; the tile is rewritten only when one
-        // of its envs began a new episode (the others' in-place writes carry the same values)
-        if (!__syncthreads_or(full)) return;
-    } else {
-        __syncthreads();
+    __syncthreads();
+    EP_MARK(1);
+    const int lane = tid & 31, warp = tid >> 5;
+    uint32_t fl = 0;
+    for (int j = lane; j < nE; j += 32) fl |= tflags[j];
+    fl = __reduce_or_sync(0xffffffffu, fl);                       // the same in every warp of the CTA
+    const bool any_snap = (fl & PA_SNAPSHOT) != 0;
+    const bool any_obs = p.obs.base_dev || p.obs.color_dev || p.obs.info_dev;
+    // persistent observation (update = SPARC_OBS_DELTA): phase A has touched the cells that changed; the tile is
+    // rewritten only when one of its envs began a new episode (the others' in-place writes carry the same values)
+    const bool encode = any_obs && !(p.mode == 0 && p.obs.update == SPARC_OBS_DELTA && !(fl & PA_NEW_EPISODE));
+    if (any_snap && warp == CTA_THREADS / 32 - 1) {               // ---- the validator warp
+        unsigned long long pass = 0;
+        for (int j = lane; j < nE; j += 32)
+            if (tflags[j] & PA_SNAPSHOT) {
+                const uint32_t* q = snaps + j * SPARC_VQ_WORDS;
+                pass += (unsigned long long)(validate_snapshot(p, q) & (int)q[3]);
+            }
+        pass = __reduce_add_sync(0xffffffffu, (unsigned)pass);
+        if (lane == 0 && pass) atomicAdd(p.sd.stats + (size_t)(blockIdx.x % SPARC_STAT_ROWS) * SPARC_N_STATS + SPARC_STAT_RULES_PASS, pass);
+        return;
     }
-    encode_tile_stage1a(st, head, flats, p.tile, nE, p.obs, tid, CTA_THREADS);
-    __syncthreads();
-    encode_tile_stage1b<FMT>(st, head, flats, p.tile, nE, p.obs, tid, CTA_THREADS);
-    __syncthreads();
-    encode_tile_stage2<FMT>(st, head, flats, p.tile, nE, env0, p.obs, tid, CTA_THREADS);
+    if (!encode) return;
+    const int nthr = any_snap ? CTA_THREADS - 32 : CTA_THREADS;   // the encoding threads
+    encode_tile_stage1<FMT>(st, head, flats, p.tile, nE, p.obs, tid, nthr);
+    if (any_snap) asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory"); else __syncthreads();
+    EP_MARK(2);
+    encode_tile_stage2<FMT>(st, head, flats, p.tile, nE, env0, p.obs, tid, nthr);
+    EP_END();
 }
 
 // ---- split pair for big batches: k_dyn (latency bound) || k_encode (bandwidth bound) -------------
@@ -298,9 +345,7 @@ __global__ void __launch_bounds__(ENC_THREADS, ENC_MINBLOCKS) k_encode(const KPa
         write_dyn(st, head, tid, e);
     }
     __syncthreads();
-    encode_tile_stage1a(st, head, flats, p.tile, nE, p.obs, tid, ENC_THREADS);
-    __syncthreads();
-    encode_tile_stage1b<FMT>(st, head, flats, p.tile, nE, p.obs, tid, ENC_THREADS);
+    encode_tile_stage1<FMT>(st, head, flats, p.tile, nE, p.obs, tid, ENC_THREADS);
     __syncthreads();
     encode_tile_stage2<FMT>(st, head, flats, p.tile, nE, env0, p.obs, tid, ENC_THREADS);
 }
@@ -348,7 +393,7 @@ __global__ void __launch_bounds__(ENC_THREADS) k_post(const KParams p) {
             write_dyn(st, head, 0, e);
         }
         __syncwarp();
-        encode_tile_stage1a(st, head, flats, 1, 1, p.obs, lane, 32);
+        encode_tile_stage1<FMT>(st, head, flats, 1, 1, p.obs, lane, 32);
         __syncwarp();
         encode_env_elementwise<FMT>(st, head, flats, env, p.obs, lane, 32);
         __syncwarp();                                            // the rows are reused by the next pass
@@ -450,9 +495,9 @@ int sparc_store_create(const SparcStoreDesc* desc, int device, SparcStore** out)
     d.inv_S = (uint32_t)((1ull << 32) / (uint64_t)d.S) + 1u;
     d.inv_4S = (uint32_t)((1ull << 32) / (uint64_t)(4 * d.S)) + 1u;
     d.Wc = (4 * d.S + 31) / 32;
-    d.inv_wsb = (uint32_t)((1ull << 32) / (uint64_t)(d.W + 2)) + 1u;
-    d.inv_wsc = (uint32_t)((1ull << 32) / (uint64_t)(d.Wc + 2)) + 1u;
-    d.inv_wsz = (uint32_t)((1ull << 32) / (uint64_t)(d.nv + 2)) + 1u;
+    { const uint64_t k0b = (uint64_t)(d.L >> 5), k0c = (uint64_t)((4 * d.S) >> 5), k0z = (uint64_t)(d.S >> 5);
+      d.inv_k0b = k0b ? (uint32_t)((1ull << 32) / k0b) + 1u : 0u; d.inv_k0c = k0c ? (uint32_t)((1ull << 32) / k0c) + 1u : 0u;
+      d.inv_k0z = k0z ? (uint32_t)((1ull << 32) / k0z) + 1u : 0u; }
     memcpy(s->plane_ids, desc->plane_ids, sizeof(s->plane_ids));
     const size_t n = desc->n_puzzles;
     int rc;
@@ -548,7 +593,7 @@ int sparc_env_create(SparcStore* store, int64_t n_envs, int traceback, int max_s
             int tmax = e->tile > e->enc_tile ? e->tile : e->enc_tile;
             if (tmax < 32) tmax = 32;                               // compact default
             tmax = compact_tile(tmax);
-            const size_t shmem = (size_t)(tile_head_words(tmax) + tile_flat_words(store->d, tmax)) * sizeof(uint32_t);
+            const size_t shmem = (size_t)(tile_head_words(tmax) + tile_flat_words(store->d, tmax) + tile_snap_words(tmax)) * sizeof(uint32_t);
             if (shmem > 48 * 1024) {
                 cudaError_t ae = cudaFuncSetAttribute(k_env<SPARC_OBS_REFERENCE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem);
                 if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_env<SPARC_OBS_COMPACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem);
@@ -717,7 +762,7 @@ static int launch_env(SparcEnv* e, KParams& p, void* stream) {
         return SPARC_OK;
     }
     {
-        const size_t shmem = (size_t)(tile_head_words(p.tile) + tile_flat_words(p.st, p.tile)) * sizeof(uint32_t);
+        const size_t shmem = (size_t)(tile_head_words(p.tile) + tile_flat_words(p.st, p.tile) + tile_snap_words(p.tile)) * sizeof(uint32_t);
         if (compact) k_env<SPARC_OBS_COMPACT><<<ntiles, CTA_THREADS, shmem, (cudaStream_t)stream>>>(p);
         else k_env<SPARC_OBS_REFERENCE><<<ntiles, CTA_THREADS, shmem, (cudaStream_t)stream>>>(p);
     }
@@ -926,6 +971,19 @@ int sparc_debug_valprof(uint64_t* out8_host, int clear) {     /* -DVAL_PROFILE b
 #else
     (void)out8_host; (void)clear;
     return fail(SPARC_E_ARG, "not a -DVAL_PROFILE build%s");
+#endif
+}
+
+int sparc_debug_envprof(uint64_t* out16_host, int clear) {    /* -DENV_PROFILE builds only: see EP_* above, tools/envprof.py */
+#ifdef ENV_PROFILE
+    if (!out16_host) return fail(SPARC_E_ARG, "null argument%s");
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpyFromSymbol(out16_host, g_envprof, 16 * sizeof(uint64_t)));
+    if (clear) { unsigned long long z[16] = {0}; z[11] = ~0ull; CU(cudaMemcpyToSymbol(g_envprof, z, sizeof(z))); }
+    return SPARC_OK;
+#else
+    (void)out16_host; (void)clear;
+    return fail(SPARC_E_ARG, "not a -DENV_PROFILE build%s");
 #endif
 }
 

@@ -104,7 +104,7 @@ struct StoreDev {
     int nv;                        // words of one dense plane: ceil(S/32)
     int Wc;                        // words of the 4-bit colour string: ceil(4S/32)
     uint32_t inv_L, inv_S, inv_4S; // floor(2^32/d)+1: exact x/d by one mul-hi for the x used here
-    uint32_t inv_wsb, inv_wsc, inv_wsz;   // same for the row strides W+2, Wc+2, nv+2
+    uint32_t inv_k0b, inv_k0c, inv_k0z;   // same for the whole words of one env's strings: L/32, 4S/32, S/32 (0 when there is none)
     const SparcPuzzleHeader* hdr;
     const uint32_t* nb;            // [n][SPARC_N_NODE_BOARDS][8]
     const uint64_t* cb;            // [n][SPARC_N_CELL_BOARDS]
@@ -225,21 +225,29 @@ SPARC_HD void env_reset(EnvRegs& e, const StoreDev& st, uint32_t puzzle) {
 // ---------------------------------------------------------------------------------------------
 // dynamics (SG.py:1024-1051 legality, 1111-1223 step)
 // ---------------------------------------------------------------------------------------------
-// bit a of the result: action a is legal from (x, y); (px, py) = path[-2] or (-1,-1)
-SPARC_HD int legal_actions(const StoreDev& st, const uint32_t (&walk)[8], const uint32_t (&v)[8],
-                           int x, int y, int px, int py) {
+// Legality (SG.py:1024-1051) on ONE board: avail = walk & ~visited (in this puzzle's lattice, not a gap, not yet on the
+// path).  A move is legal when its target is available, or -- traceback -- when it is path[-2] (node index pn, or -1)
+// and that node is walkable (prev_ok; it is, unless the start node itself sits on a gap).  One dynamic bit test per
+// direction instead of two: the 8-way word selects of board_bit were half of the dynamics' instructions
+// (profiles/r2_kernels_ncu_config2.txt, tools/envprof.py).
+SPARC_HD void board_avail(uint32_t (&avail)[8], const uint32_t (&walk)[8], const uint32_t (&v)[8]) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) avail[k] = walk[k] & ~v[k];
+}
+// bit a of the result: action a is legal from (x, y)
+SPARC_HD int legal_actions(const StoreDev& st, const uint32_t (&avail)[8], int x, int y, int pn, bool prev_ok) {
     int mask = 0;
 #pragma unroll
     for (int a = 0; a < 4; a++) {
         const int nx = x + dir_dx(a), ny = y + dir_dy(a);
         if ((unsigned)nx >= (unsigned)st.SX || (unsigned)ny >= (unsigned)st.SY) continue;
         const int n = nx * st.SY + ny;
-        if (!board_bit(walk, n)) continue;                 // out of this puzzle's lattice, or a gap
-        const int fresh = !board_bit(v, n);
-        if (fresh || (nx == px && ny == py)) mask |= 1 << a;
+        if (board_bit(avail, n) || (n == pn && prev_ok)) mask |= 1 << a;
     }
     return mask;
 }
+// node index of path[-2] from the position and the move that led there (d = top of the move stack)
+SPARC_HD int prev_node(const StoreDev& st, int x, int y, int d) { return (x - dir_dx(d)) * st.SY + (y - dir_dy(d)); }
 
 // top of the move stack = the move that led to path[-1]; path length = plen
 SPARC_HD int stack_top(const StateDev& sd, long long n, long long i, int plen) {
@@ -250,31 +258,25 @@ SPARC_HD int stack_top(const StateDev& sd, long long n, long long i, int plen) {
 SPARC_HD void env_step(EnvRegs& e, const StoreDev& st, const StateDev& sd, const StepCfg& cfg, long long i,
                        long long action, StepResult& r) {
     const HdrRegs h = load_hdr(st, e.puzzle);
-    uint32_t walk[8];
+    uint32_t walk[8], avail[8];
     load_board(walk, st.nb + ((size_t)e.puzzle * SPARC_N_NODE_BOARDS + SPARC_NB_WALK) * 8);
     int plen = board_popc(e.v);                            // path nodes are distinct, visited == set(path)
     const int tb = cfg.traceback && sd.moves != nullptr;
-    int px = -1, py = -1;
-    if (tb && plen >= 2) { const int d = stack_top(sd, cfg.n_envs, i, plen); px = e.x - dir_dx(d); py = e.y - dir_dy(d); }
+    int pn = -1;                                           // path[-2] as a node index
+    if (tb && plen >= 2) pn = prev_node(st, e.x, e.y, stack_top(sd, cfg.n_envs, i, plen));
+    bool prev_ok = pn >= 0 && board_bit(walk, pn);
+    board_avail(avail, walk, e.v);
 
     e.step += 1;                                           // SG.py:1132 (illegal actions count too)
     int truncated = (int)e.step >= cfg.max_steps;          // SG.py:1134
     int moved = 0;
-    const int legal_now = legal_actions(st, walk, e.v, e.x, e.y, px, py);
-    if (action >= 0 && action < 4 && ((legal_now >> (int)action) & 1)) {
+    if (action >= 0 && action < 4) {
         const int a = (int)action;
         const int nx = e.x + dir_dx(a), ny = e.y + dir_dy(a);
         const int n = nx * st.SY + ny;
-        if (board_bit(e.v, n)) {                           // traceback undo (SG.py:1141-1166)
-            board_flip(e.v, e.x * st.SY + e.y);
-            if (e.on_depth == plen) {                      // cursor leaves the popped node
-                e.tnode = sp_ldg(st.trie + (size_t)e.tnode * SPARC_TRIE_NODE_WORDS + 4);
-                e.on_depth = plen - 1;
-            }
-            plen -= 1;
-            px = -1; py = -1;
-            if (plen >= 2) { const int d = stack_top(sd, cfg.n_envs, i, plen); px = nx - dir_dx(d); py = ny - dir_dy(d); }
-        } else {                                           // fresh node (SG.py:1167-1188)
+        const bool inside = (unsigned)nx < (unsigned)st.SX && (unsigned)ny < (unsigned)st.SY;
+        const bool fresh = inside && board_bit(avail, n);
+        if (fresh) {                                       // fresh node (SG.py:1167-1188)
             board_flip(e.v, n);
             if (e.on_depth == plen) {
                 const uint32_t child = sp_ldg(st.trie + (size_t)e.tnode * SPARC_TRIE_NODE_WORDS + a);
@@ -285,16 +287,27 @@ SPARC_HD void env_step(EnvRegs& e, const StoreDev& st, const StateDev& sd, const
                 uint32_t* wp = sd.moves + (long long)(idx >> 4) * cfg.n_envs + i;
                 const int sh = (idx & 15) * 2;
                 *wp = (*wp & ~(3u << sh)) | ((uint32_t)a << sh);
+                pn = e.x * st.SY + e.y; prev_ok = board_bit(walk, pn);
             }
             plen += 1;
-            px = e.x; py = e.y;
-            if (!tb) { px = -1; py = -1; }
+            e.x = nx; e.y = ny;
+            moved = 1;
+        } else if (inside && n == pn && prev_ok) {         // traceback undo (SG.py:1141-1166)
+            board_flip(e.v, e.x * st.SY + e.y);
+            if (e.on_depth == plen) {                      // cursor leaves the popped node
+                e.tnode = sp_ldg(st.trie + (size_t)e.tnode * SPARC_TRIE_NODE_WORDS + 4);
+                e.on_depth = plen - 1;
+            }
+            plen -= 1;
+            pn = -1; prev_ok = false;
+            if (plen >= 2) { pn = prev_node(st, nx, ny, stack_top(sd, cfg.n_envs, i, plen)); prev_ok = board_bit(walk, pn); }
+            e.x = nx; e.y = ny;
+            moved = 1;
         }
-        e.x = nx; e.y = ny;
-        moved = 1;
+        if (moved) board_avail(avail, walk, e.v);
     }
     const int terminated = (e.x == h.tx && e.y == h.ty);   // SG.py:1192
-    const int legal_after = legal_actions(st, walk, e.v, e.x, e.y, px, py);
+    const int legal_after = legal_actions(st, avail, e.x, e.y, pn, prev_ok);
     if (legal_after == 0) truncated = 1;                   // SG.py:1195-1196
     if (terminated) truncated = 0;                         // SG.py:1198-1199
     const int on_trie = (e.on_depth == plen) && e.tnode != 0;
@@ -317,14 +330,14 @@ SPARC_HD void env_step(EnvRegs& e, const StoreDev& st, const StateDev& sd, const
 
 // legal mask of the current state without stepping (reset / frozen envs)
 SPARC_HD int env_legal_now(const EnvRegs& e, const StoreDev& st, const StateDev& sd, const StepCfg& cfg, long long i) {
-    uint32_t walk[8];
+    uint32_t walk[8], avail[8];
     load_board(walk, st.nb + ((size_t)e.puzzle * SPARC_N_NODE_BOARDS + SPARC_NB_WALK) * 8);
     const int plen = board_popc(e.v);
-    int px = -1, py = -1;
-    if (cfg.traceback && sd.moves != nullptr && plen >= 2) {
-        const int d = stack_top(sd, cfg.n_envs, i, plen); px = e.x - dir_dx(d); py = e.y - dir_dy(d);
-    }
-    return legal_actions(st, walk, e.v, e.x, e.y, px, py);
+    int pn = -1;
+    if (cfg.traceback && sd.moves != nullptr && plen >= 2) pn = prev_node(st, e.x, e.y, stack_top(sd, cfg.n_envs, i, plen));
+    const bool prev_ok = pn >= 0 && board_bit(walk, pn);
+    board_avail(avail, walk, e.v);
+    return legal_actions(st, avail, e.x, e.y, pn, prev_ok);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -953,6 +966,7 @@ SPARC_HD int validate_env(const StoreDev& st, uint32_t puzzle, const uint32_t* v
 //   dyn : SPARC_DYN_STRIDE words per env: visited plane (dense, 8 words) + bit index of the agent
 // ---------------------------------------------------------------------------------------------
 #define SPARC_DYN_STRIDE 9
+#define SPARC_VQ_WORDS 12     // a state to validate: env, puzzle, x | y << 8, counts-for-RULES_PASS, visited[8]
 
 SPARC_HD void write_dyn(const StoreDev& st, uint32_t* dyn, int j, const EnvRegs& e) {
     uint32_t* row = dyn + j * SPARC_DYN_STRIDE;
@@ -1014,45 +1028,44 @@ struct InfoNzSrc {                      // additional_info != 0, 1 bit per node
     SPARC_HD uint32_t word(int j, int k) const { return raw(j, k); }
 };
 
-// stage 1a (cooperative): rows[j][k] = word k of env j's string, k in [0, W+1] (zeros behind the string).
-// Four row words per thread per pass, all global loads issued before any is used.  (Rows used to be stored
-// shifted by (j*L) mod 32 so that a chunk was one LDS + one shift; every row word then cost two loads, two
-// fix-ups and a funnel shift -- ~80 instructions, a quarter of k_encode<reference> and half of k_encode<compact>.
-// Plain rows cost ~20 per word and one more LDS + a funnel shift per fetch.)
+// stage 1 (cooperative): rows[j][k] = word k of env j's string, k in [0, W+1] (zeros behind the string), and -- in the
+// words from k0 = L/32 on -- the first bits of env j+1 that belong to env j's last chunk (the "tail"; A = stream bits
+// per 16-byte chunk, a power of two <= 32).  Two parts, no barrier between them: the whole words [0, k0) of every row,
+// four per thread per pass with all global loads issued before any is used; then the two or three last words of row j
+// by one thread (counted from the end of the CTA: the first threads ran phase A in the fused kernel), which also
+// fetches word 0 of env j+1.  (Rows used to be stored shifted by (j*L) mod 32 so that a chunk was one LDS + one shift;
+// every row word then cost two loads, two fix-ups and a funnel shift -- ~80 instructions, a quarter of
+// k_encode<reference> and half of k_encode<compact>.  Plain rows cost ~20 per word and one more LDS + a funnel shift
+// per fetch.  The tails used to be a second stage behind a barrier: ~450 instructions in ONE warp, 0.7 us of the
+// small-batch kernel's critical path -- tools/envprof.py; folded into every word of the first part they cost the
+// issue-bound compact encoder 7 us of 60.)
 template <class Src>
-SPARC_HD void build_rows(const Src& src, uint32_t* rows, int nE, uint32_t inv_ws, int tid, int nthr) {
-    const int Ws = src.W() + 2;
-    const int total = nE * Ws;
+SPARC_HD void build_rows(const Src& src, uint32_t* rows, int nE, uint32_t inv_k0, int A, int tid, int nthr) {
+    const int L = src.L(), Ws = src.W() + 2;
+    const int k0 = L >> 5, sh = L & 31;                         // row-bit L: right behind env j's own bits
+    const int total = nE * k0;
     for (int base = tid; base < total; base += 4 * nthr) {
         int j[4], k[4];
         uint32_t w[4];
 #pragma unroll
         for (int u = 0; u < 4; u++) {
             const int idx = base + u * nthr;
-            j[u] = (int)sp_umulhi((uint32_t)idx, inv_ws); k[u] = idx - j[u] * Ws;
+            j[u] = k0 == 1 ? idx : (int)sp_umulhi((uint32_t)idx, inv_k0); k[u] = idx - j[u] * k0;   // (2^32 / 1 + 1 does not fit)
             w[u] = idx < total ? src.raw(j[u], k[u]) : 0u;
         }
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const int idx = base + u * nthr;
-            if (idx < total) rows[idx] = src.fix(j[u], k[u], w[u]);
-        }
+        for (int u = 0; u < 4; u++)
+            if (base + u * nthr < total) rows[j[u] * Ws + k[u]] = src.fix(j[u], k[u], w[u]);
     }
-}
-// stage 1b (one thread per env, after a barrier): append to row j the first bits of env j+1 that
-// belong to env j's last chunk.  A = bits per 16-byte chunk of this stream.
-template <class Src>
-SPARC_HD void build_tails(const Src& src, uint32_t* rows, int nE, int A, int tid, int nthr) {
-    const int L = src.L(), Ws = src.W() + 2;
-    for (int j = tid; j + 1 < nE; j += nthr) {
-        const int end = (j + 1) * L;                            // first stream bit of env j+1
-        const int tb = (A - (end % A)) % A;
-        if (!tb) continue;
-        const uint32_t bits = src.word(j + 1, 0) & (tb >= 32 ? 0xFFFFFFFFu : (1u << tb) - 1u);
-        uint32_t* r = rows + j * Ws + (L >> 5);                 // row-bit L: right behind env j's own bits
-        const int sh = L & 31;
-        r[0] |= bits << sh;
-        if (sh) r[1] |= bits >> (32 - sh);
+    for (int j = nthr - 1 - tid; j < nE; j += nthr) {
+        const bool more = j + 1 < nE;
+        const uint32_t w0 = src.raw(j, k0), w1 = src.raw(j, k0 + 1), w2 = src.raw(j, k0 + 2), t = more ? src.raw(j + 1, 0) : 0u;
+        const int tb = (A - (((j + 1) * L) & (A - 1))) & (A - 1);             // bits of env j+1 in env j's last chunk
+        const uint32_t bits = more ? src.fix(j + 1, 0, t) & ((1u << tb) - 1u) : 0u;
+        uint32_t* r = rows + j * Ws + k0;
+        r[0] = src.fix(j, k0, w0) | (bits << sh);
+        r[1] = src.fix(j, k0 + 1, w1) | (sh ? bits >> (32 - sh) : 0u);
+        if (k0 + 2 < Ws) r[2] = src.fix(j, k0 + 2, w2);
     }
 }
 // stage 2 (cooperative): expand.  g = first stream bit of the chunk -> (env j, row bit); returns the 32 stream
@@ -1176,25 +1189,16 @@ template <> struct ObsTypes<SPARC_OBS_COMPACT> { typedef uint8_t base_t; typedef
 
 // shared-memory words: per-tile header (dyn rows + puzzle ids) and the three row sets
 SPARC_HD int tile_head_words(int tile) { return tile * (SPARC_DYN_STRIDE + 1); }
+// the fused k_env also keeps, behind the rows: per-env flags of phase A (PA_*) and the snapshots its validator warp works on
+SPARC_HD int tile_snap_words(int tile) { return tile * (1 + SPARC_VQ_WORDS); }
 SPARC_HD int tile_flat_words(const StoreDev& st, int tile) { return tile * ((st.W + 2) + (st.Wc + 2) + (st.nv + 2)); }
-// encoder for one tile: stage 1a, barrier, stage 1b, barrier, stage 2 (barriers among the nthr
-// encoding threads).  head = dyn[tile][9] | tile_puzzle[tile]; flats = base rows | colour rows | info rows
-SPARC_HD void encode_tile_stage1a(const StoreDev& st, const uint32_t* head, uint32_t* flats, int tile, int nE,
-                                  const SparcObsOut& obs, int tid, int nthr) {
-    const uint32_t* dyn = head;
-    const uint32_t* tile_puzzle = head + tile * SPARC_DYN_STRIDE;
-    uint32_t* rb = flats;
-    uint32_t* rc = rb + tile * (st.W + 2);
-    uint32_t* rz = rc + tile * (st.Wc + 2);
-    if (obs.base_dev) build_rows(PlaneSrc{st, dyn, tile_puzzle}, rb, nE, st.inv_wsb, tid, nthr);
-    if (obs.color_dev) build_rows(ColorSrc{st, tile_puzzle}, rc, nE, st.inv_wsc, tid, nthr);
-    if (obs.info_dev) build_rows(InfoNzSrc{st, tile_puzzle}, rz, nE, st.inv_wsz, tid, nthr);
-}
+// encoder for one tile: stage 1, barrier, stage 2 (barrier among the nthr encoding threads).
+// head = dyn[tile][9] | tile_puzzle[tile]; flats = base rows | colour rows | info rows
 // FMT = SPARC_OBS_* is a compile-time constant in the kernels: the reference-format encoder carries no trace of the
 // compact one (a run-time branch here cost 4 % of k_encode: 0.170 -> 0.176 ms, measured)
 template <int FMT = SPARC_OBS_REFERENCE>
-SPARC_HD void encode_tile_stage1b(const StoreDev& st, const uint32_t* head, uint32_t* flats, int tile, int nE,
-                                  const SparcObsOut& obs, int tid, int nthr) {
+SPARC_HD void encode_tile_stage1(const StoreDev& st, const uint32_t* head, uint32_t* flats, int tile, int nE,
+                                 const SparcObsOut& obs, int tid, int nthr) {
     const uint32_t* dyn = head;
     const uint32_t* tile_puzzle = head + tile * SPARC_DYN_STRIDE;
     uint32_t* rb = flats;
@@ -1203,9 +1207,9 @@ SPARC_HD void encode_tile_stage1b(const StoreDev& st, const uint32_t* head, uint
     // stream bits per fetch of the expand loops: 16-byte chunks of int32 / int32 / int64, or (compact) uint8 /
     // uint8 fetched as two 32-bit halves / int32
     constexpr bool cp = FMT == SPARC_OBS_COMPACT;
-    if (obs.base_dev) build_tails(PlaneSrc{st, dyn, tile_puzzle}, rb, nE, cp ? 16 : 4, tid, nthr);
-    if (obs.color_dev) build_tails(ColorSrc{st, tile_puzzle}, rc, nE, cp ? 32 : 16, tid, nthr);
-    if (obs.info_dev) build_tails(InfoNzSrc{st, tile_puzzle}, rz, nE, cp ? 4 : 2, tid, nthr);
+    if (obs.base_dev) build_rows(PlaneSrc{st, dyn, tile_puzzle}, rb, nE, st.inv_k0b, cp ? 16 : 4, tid, nthr);
+    if (obs.color_dev) build_rows(ColorSrc{st, tile_puzzle}, rc, nE, st.inv_k0c, cp ? 32 : 16, tid, nthr);
+    if (obs.info_dev) build_rows(InfoNzSrc{st, tile_puzzle}, rz, nE, st.inv_k0z, cp ? 4 : 2, tid, nthr);
 }
 template <int FMT = SPARC_OBS_REFERENCE>
 SPARC_HD void encode_tile_stage2(const StoreDev& st, const uint32_t* head, const uint32_t* flats, int tile, int nE,
@@ -1281,7 +1285,6 @@ struct KParams {
     uint32_t* rq_count;      // delta observations: number of envs that began a new episode this step (nullptr in the
     uint32_t* rq;            // fused kernel, which decides per tile); [n_envs] their indices -> k_encode_list
 };
-#define SPARC_VQ_WORDS 12
 
 SPARC_HD long long load_action(const void* p, int dtype, long long i) {
     if (dtype == SPARC_ACT_U8) return reinterpret_cast<const uint8_t*>(p)[i];
@@ -1313,15 +1316,19 @@ SPARC_HD void obs_delta_planes(T* base, const StoreDev& st, long long i, int ox,
 // `full` (optional): set when the env began a new episode in this call, i.e. its whole observation changed.
 // MAY_DELTA = false compiles the in-place observation update out (k_dyn of the full-rewrite step: 62 registers
 // instead of 66, i.e. 8 instead of 7 resident CTAs per SM).
+enum { PA_NEW_EPISODE = 1, PA_SNAPSHOT = 2 };
 template <bool INLINE_VALIDATION = true, bool MAY_DELTA = true>
 SPARC_HD bool phase_a(const KParams& p, long long i, EnvRegs& e, uint32_t* scratch, unsigned long long* stats,
-                      bool* full = nullptr) {
+                      int* tile_flags = nullptr, uint32_t* snap = nullptr) {
+    // tile_flags (the fused k_env): PA_NEW_EPISODE | PA_SNAPSHOT of this env.  snap: SPARC_VQ_WORDS words of the CTA's
+    // shared memory; a state that needs validating is stored there instead of being validated by this thread, and
+    // another warp of the CTA validates it beside the encoder (validate_snapshot).
     const StoreDev& st = p.st;
     const long long n = p.cfg.n_envs;
     load_env(e, p.sd, st, n, i);
     StepResult r;
     r.reward_code = SPARC_R_ZERO; r.terminated = 0; r.truncated = 0; r.legal_mask = 0; r.rule_flags = 0;
-    bool need_legal = false, have_stats = false, new_episode = false;
+    bool need_legal = false, have_stats = false, new_episode = false, snapped = false;
     const int ox = (int)e.x, oy = (int)e.y;
     if (p.mode == 1) {                                                   // ---- reset (SG.py:1057-1108)
         const bool sel = p.reset_mask ? p.reset_mask[i] != 0 : true;
@@ -1351,7 +1358,12 @@ SPARC_HD bool phase_a(const KParams& p, long long i, EnvRegs& e, uint32_t* scrat
         const bool done = r.terminated || r.truncated;
         if (p.cfg.validate_mode == SPARC_VALIDATE_EVERY_STEP ||
             (p.cfg.validate_mode == SPARC_VALIDATE_TERMINAL && done)) {
-            if (!INLINE_VALIDATION || (p.vq_count && p.cfg.validate_mode == SPARC_VALIDATE_TERMINAL)) {
+            if (snap) {
+                snap[0] = (uint32_t)i; snap[1] = e.puzzle; snap[2] = (uint32_t)e.x | ((uint32_t)e.y << 8); snap[3] = done;     // [3]: counts for RULES_PASS
+#pragma unroll
+                for (int k = 0; k < 8; k++) snap[4 + k] = e.v[k];
+                snapped = true;
+            } else if (!INLINE_VALIDATION || (p.vq_count && p.cfg.validate_mode == SPARC_VALIDATE_TERMINAL)) {
                 // Terminal states are rare (1-2 % of the envs per step) and validating one inline idles
                 // the 31 other lanes of its warp for the whole flood fill: queue a snapshot instead;
                 // validate_queued() runs densely packed, beside the observation encoder.
@@ -1396,7 +1408,7 @@ SPARC_HD bool phase_a(const KParams& p, long long i, EnvRegs& e, uint32_t* scrat
         store_env(e, p.sd, st, n, i);
     }
     if (need_legal) r.legal_mask = env_legal_now(e, st, p.sd, p.cfg, i);
-    if (full) *full = new_episode;
+    if (tile_flags) *tile_flags = (new_episode ? PA_NEW_EPISODE : 0) | (snapped ? PA_SNAPSHOT : 0);
     if (MAY_DELTA && p.mode == 0 && p.obs.update == SPARC_OBS_DELTA) {   // persistent observation, touched in place
         if (new_episode) {
             if (p.rq_count) {                                            // whole observation: k_encode_list rewrites it
@@ -1418,7 +1430,7 @@ SPARC_HD bool phase_a(const KParams& p, long long i, EnvRegs& e, uint32_t* scrat
     if (p.out.terminated_dev) p.out.terminated_dev[i] = (uint8_t)r.terminated;
     if (p.out.truncated_dev) p.out.truncated_dev[i] = (uint8_t)r.truncated;
     if (p.out.legal_mask_dev) p.out.legal_mask_dev[i] = (uint8_t)r.legal_mask;
-    if (p.out.rule_flags_dev) p.out.rule_flags_dev[i] = (uint16_t)r.rule_flags;
+    if (p.out.rule_flags_dev && !snapped) p.out.rule_flags_dev[i] = (uint16_t)r.rule_flags;     // (snapped: validate_snapshot writes them)
     if (p.out.step_count_dev) p.out.step_count_dev[i] = (int32_t)e.step;
     if (p.out.agent_xy_dev) { p.out.agent_xy_dev[2 * i] = (uint8_t)e.x; p.out.agent_xy_dev[2 * i + 1] = (uint8_t)e.y; }
     return have_stats;
@@ -1427,8 +1439,7 @@ SPARC_HD bool phase_a(const KParams& p, long long i, EnvRegs& e, uint32_t* scrat
 // deferred terminal validation of queue entry `slot` (one thread): writes the env's rule flags, returns 1 when all
 // rules are satisfied (for the RULES_PASS statistic), 0 when not, -1 when an exact-fit search outgrew `fit_budget`
 // (nothing written: the snapshot becomes a hard item)
-SPARC_HD int validate_queued(const KParams& p, uint32_t slot, int fit_budget = 0) {
-    const uint32_t* q = p.vq + (size_t)slot * SPARC_VQ_WORDS;
+SPARC_HD int validate_snapshot(const KParams& p, const uint32_t* q, int fit_budget = 0) {
     uint32_t vd[SPARC_DYN_STRIDE];
 #pragma unroll
     for (int k = 0; k < 8; k++) vd[k] = q[4 + k];
@@ -1438,4 +1449,7 @@ SPARC_HD int validate_queued(const KParams& p, uint32_t slot, int fit_budget = 0
     f |= SPARC_RULE_VALID;
     if (p.out.rule_flags_dev) p.out.rule_flags_dev[q[0]] = (uint16_t)f;
     return (f & SPARC_RULE_ALL) != 0;
+}
+SPARC_HD int validate_queued(const KParams& p, uint32_t slot, int fit_budget = 0) {
+    return validate_snapshot(p, p.vq + (size_t)slot * SPARC_VQ_WORDS, fit_budget);
 }

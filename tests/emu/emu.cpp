@@ -17,9 +17,9 @@ static StoreDev make_store(const SparcStoreDesc* d) {
     s.inv_S = (uint32_t)((1ull << 32) / (uint64_t)s.S) + 1u;
     s.inv_4S = (uint32_t)((1ull << 32) / (uint64_t)(4 * s.S)) + 1u;
     s.Wc = (4 * s.S + 31) / 32;
-    s.inv_wsb = (uint32_t)((1ull << 32) / (uint64_t)(s.W + 2)) + 1u;
-    s.inv_wsc = (uint32_t)((1ull << 32) / (uint64_t)(s.Wc + 2)) + 1u;
-    s.inv_wsz = (uint32_t)((1ull << 32) / (uint64_t)(s.nv + 2)) + 1u;
+    { const uint64_t k0b = (uint64_t)(s.L >> 5), k0c = (uint64_t)((4 * s.S) >> 5), k0z = (uint64_t)(s.S >> 5);
+      s.inv_k0b = k0b ? (uint32_t)((1ull << 32) / k0b) + 1u : 0u; s.inv_k0c = k0c ? (uint32_t)((1ull << 32) / k0c) + 1u : 0u;
+      s.inv_k0z = k0z ? (uint32_t)((1ull << 32) / k0z) + 1u : 0u; }
     s.hdr = d->headers; s.nb = d->node_boards; s.cb = d->cell_boards; s.sbits = d->static_bits;
     s.color4 = d->color4; s.info_nz = d->info_nz; s.info = d->info; s.shapes = d->shapes; s.trie = d->trie; s.vrec = nullptr;
     return s;
@@ -56,30 +56,41 @@ int emu_launch(const SparcStoreDesc* desc, uint32_t* core, uint32_t* vis, int32_
     if (delta && defer_validation) { rq.resize((size_t)n_envs); p.rq = rq.data(); p.rq_count = &rq_count; }
     const StoreDev& st = p.st;
     // exactly the dynamic shared memory the kernels request: an out-of-bounds row access is an ASan error
-    std::vector<uint32_t> smem((size_t)tile_head_words(tile) + tile_flat_words(st, tile), 0xDEADBEEFu);
+    std::vector<uint32_t> smem((size_t)tile_head_words(tile) + tile_flat_words(st, tile) + tile_snap_words(tile), 0xDEADBEEFu);
     std::vector<EnvRegs> regs(tile);
     for (long long env0 = 0; env0 < n_envs; env0 += tile) {
         const int nE = (int)((n_envs - env0) < tile ? (n_envs - env0) : tile);
         uint32_t* dyn = smem.data();
         uint32_t* tile_puzzle = dyn + (size_t)tile * SPARC_DYN_STRIDE;
+        uint32_t* tflags = dyn + tile_head_words(tile) + tile_flat_words(st, tile);
+        uint32_t* snaps = tflags + tile;
         bool any_full = false;
         for (int tid = 0; tid < nE; tid++) {
             unsigned long long my[SPARC_N_STATS];
-            bool full = false;
-            if (phase_a(p, env0 + tid, regs[tid], dyn + tid * SPARC_DYN_STRIDE, my, &full) && mode == 0)
+            int fl = 0;
+            // the fused k_env (no global queue) leaves the states to validate in shared memory for its validator warp
+            const bool have = defer_validation ? phase_a(p, env0 + tid, regs[tid], dyn + tid * SPARC_DYN_STRIDE, my, &fl)
+                                               : phase_a<false, true>(p, env0 + tid, regs[tid], dyn + tid * SPARC_DYN_STRIDE, my, &fl,
+                                                                      snaps + tid * SPARC_VQ_WORDS);
+            if (have && mode == 0)
                 for (int k = 0; k < SPARC_N_STATS; k++) stats[k] += my[k];
-            any_full |= full;
+            tflags[tid] = (uint32_t)fl;
+            any_full |= (fl & PA_NEW_EPISODE) != 0;
             tile_puzzle[tid] = regs[tid].puzzle;
             write_dyn(st, dyn, tid, regs[tid]);
         }
+        for (int j = 0; j < nE; j++)
+            if (tflags[j] & PA_SNAPSHOT) {
+                const uint32_t* q = snaps + j * SPARC_VQ_WORDS;
+                stats[SPARC_STAT_RULES_PASS] += (unsigned long long)(validate_snapshot(p, q) & (int)q[3]);
+            }
         if (delta && (defer_validation || !any_full)) continue;
         uint32_t* flats = dyn + tile_head_words(tile);
-        for (int tid = 0; tid < nthr; tid++) encode_tile_stage1a(st, dyn, flats, tile, nE, p.obs, tid, nthr);
         if (p.obs.format == SPARC_OBS_COMPACT) {
-            for (int tid = 0; tid < nthr; tid++) encode_tile_stage1b<SPARC_OBS_COMPACT>(st, dyn, flats, tile, nE, p.obs, tid, nthr);
+            for (int tid = 0; tid < nthr; tid++) encode_tile_stage1<SPARC_OBS_COMPACT>(st, dyn, flats, tile, nE, p.obs, tid, nthr);
             for (int tid = 0; tid < nthr; tid++) encode_tile_stage2<SPARC_OBS_COMPACT>(st, dyn, flats, tile, nE, env0, p.obs, tid, nthr);
         } else {
-            for (int tid = 0; tid < nthr; tid++) encode_tile_stage1b<SPARC_OBS_REFERENCE>(st, dyn, flats, tile, nE, p.obs, tid, nthr);
+            for (int tid = 0; tid < nthr; tid++) encode_tile_stage1<SPARC_OBS_REFERENCE>(st, dyn, flats, tile, nE, p.obs, tid, nthr);
             for (int tid = 0; tid < nthr; tid++) encode_tile_stage2<SPARC_OBS_REFERENCE>(st, dyn, flats, tile, nE, env0, p.obs, tid, nthr);
         }
     }
@@ -94,7 +105,7 @@ int emu_launch(const SparcStoreDesc* desc, uint32_t* core, uint32_t* vis, int32_
             load_env(e, p.sd, st, n_envs, env);
             head[SPARC_DYN_STRIDE] = e.puzzle;
             write_dyn(st, head, 0, e);
-            for (int tid = 0; tid < nthr; tid++) encode_tile_stage1a(st, head, flats, 1, 1, p.obs, tid, nthr);
+            for (int tid = 0; tid < nthr; tid++) encode_tile_stage1(st, head, flats, 1, 1, p.obs, tid, nthr);
             for (int tid = 0; tid < nthr; tid++) {
                 if (p.obs.format == SPARC_OBS_COMPACT) encode_env_elementwise<SPARC_OBS_COMPACT>(st, head, flats, env, p.obs, tid, nthr);
                 else encode_env_elementwise<SPARC_OBS_REFERENCE>(st, head, flats, env, p.obs, tid, nthr);
