@@ -52,6 +52,11 @@ struct SparcStore {
     int plane_ids[SPARC_MAX_PLANES];
 };
 
+// sparc_step_host on launch-bound batches: the actions ride in the launch itself, two bits each (<= 8,192 envs = 2 KB of
+// kernel parameters) -- no PCIe read in front of the dynamics; see k_env_host below
+#define SPARC_PACKED_MAX_ENVS 8192
+struct PackedActions { uint32_t w[SPARC_PACKED_MAX_ENVS / 16]; };
+
 struct SparcEnv {
     SparcStore* store;
     StepCfg cfg;
@@ -80,6 +85,18 @@ struct SparcEnv {
     float* rew_stage;
     uint8_t* term_stage;
     uint8_t* trunc_stage;
+    // sparc_step_host, fused kernel: completion flag in mapped host memory (see KParams::done_flag) and the device
+    // addresses of the caller's pinned buffers as of the last call
+    volatile uint32_t* done_host;
+    uint32_t* done_dev;
+    uint32_t* done_count;
+    uint32_t done_seq;
+    bool notify;             // this launch is k_env_host: packed actions in, packed results + done flag out
+    uint8_t* packed_dev;     // [n_envs rounded up to 16] per-env result bytes
+    char* res_host;          // mapped host memory: reward f32[nb] | terminated u8[nb] | truncated u8[nb], nb = n_envs rounded up to 16
+    char* res_host_dev;
+    size_t res_nb;
+    PackedActions pa;
 };
 
 // dynamic shared memory of both kernels: tile heads (dyn rows + puzzle ids) | flat strings
@@ -144,7 +161,7 @@ __device__ __forceinline__ unsigned long long ep_ns() { unsigned long long t; as
 
 // ---- simple kernel: one CTA = one tile (small batches: every CTA is resident at once) ----------
 template <int FMT>
-__global__ void __launch_bounds__(CTA_THREADS, SPARC_MINBLOCKS) k_env(const KParams p) {
+__device__ __forceinline__ void k_env_body(const KParams& p, const uint32_t* packed_actions) {
     const StoreDev& st = p.st;
     const int tid = threadIdx.x;
     const long long env0 = (long long)blockIdx.x * p.tile;
@@ -165,8 +182,9 @@ __global__ void __launch_bounds__(CTA_THREADS, SPARC_MINBLOCKS) k_env(const KPar
     if (tid < nE) {
         // a state that needs validating is left in shared memory: warp 3 validates it while warps 0-2 encode (inline,
         // the other 127 threads of the CTA waited at the barrier for it: 10.1 -> 8.8 us per step on config 2)
-        int fl = 0;
-        have_stats = phase_a<false, true>(p, env0 + tid, e, head + tid * SPARC_DYN_STRIDE, my_stats, &fl, snaps + tid * SPARC_VQ_WORDS);
+        int fl = 0, pk = -1;
+        if (packed_actions) { const long long i = env0 + tid; pk = (int)(packed_actions[i >> 4] >> ((i & 15) * 2)) & 3; }
+        have_stats = phase_a<false, true>(p, env0 + tid, e, head + tid * SPARC_DYN_STRIDE, my_stats, &fl, snaps + tid * SPARC_VQ_WORDS, pk);
         tflags[tid] = (uint32_t)fl;
         head[p.tile * SPARC_DYN_STRIDE + tid] = e.puzzle;
         write_dyn(st, head, tid, e);
@@ -175,6 +193,39 @@ __global__ void __launch_bounds__(CTA_THREADS, SPARC_MINBLOCKS) k_env(const KPar
     if (p.mode == 0 && tid < ((nE + 31) & ~31)) reduce_stats(p, have_stats, my_stats);
     __syncthreads();
     EP_MARK(1);
+    if (p.done_flag) {
+        // sparc_step_host: every CTA counts itself once its per-env results (one packed byte each, device memory) are
+        // written; the last one copies them to the host in one coalesced sweep and releases the host, which need not
+        // wait for the observation rewrite that follows
+        __shared__ int s_last;
+        if (tid == 0) { __threadfence(); s_last = atomicAdd(p.done_count, 1u) == gridDim.x - 1; }
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            const uint4* src = reinterpret_cast<const uint4*>(p.packed_out);
+            for (int k = tid; k < (int)((n + 15) >> 4); k += CTA_THREADS) {       // 16 envs: 64 + 16 + 16 bytes over PCIe
+                const uint4 q = __ldcg(src + k);                                  // (written by other SMs: not through L1)
+                const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+                uint32_t te[4], tr[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    float4 r;
+                    r.x = reward_value(w[u] & 7); r.y = reward_value((w[u] >> 8) & 7);
+                    r.z = reward_value((w[u] >> 16) & 7); r.w = reward_value((w[u] >> 24) & 7);
+                    reinterpret_cast<float4*>(p.host_reward)[4 * k + u] = r;
+                    te[u] = (w[u] >> 3) & 0x01010101u; tr[u] = (w[u] >> 4) & 0x01010101u;
+                }
+                reinterpret_cast<uint4*>(p.host_term)[k] = make_uint4(te[0], te[1], te[2], te[3]);
+                reinterpret_cast<uint4*>(p.host_trunc)[k] = make_uint4(tr[0], tr[1], tr[2], tr[3]);
+            }
+            __syncthreads();
+            if (tid == 0) {
+                *p.done_count = 0;
+                __threadfence_system();
+                *reinterpret_cast<volatile uint32_t*>(p.done_flag) = p.done_seq;
+            }
+        }
+    }
     const int lane = tid & 31, warp = tid >> 5;
     uint32_t fl = 0;
     for (int j = lane; j < nE; j += 32) fl |= tflags[j];
@@ -203,6 +254,10 @@ __global__ void __launch_bounds__(CTA_THREADS, SPARC_MINBLOCKS) k_env(const KPar
     encode_tile_stage2<FMT>(st, head, flats, p.tile, nE, env0, p.obs, tid, nthr);
     EP_END();
 }
+template <int FMT>
+__global__ void __launch_bounds__(CTA_THREADS, SPARC_MINBLOCKS) k_env(const KParams p) { k_env_body<FMT>(p, nullptr); }
+template <int FMT>
+__global__ void __launch_bounds__(CTA_THREADS, SPARC_MINBLOCKS) k_env_host(const KParams p, const PackedActions pa) { k_env_body<FMT>(p, pa.w); }
 
 // ---- split pair for big batches: k_dyn (latency bound) || k_encode (bandwidth bound) -------------
 // The observation is a pure function of the env state, so the step splits into a dynamics kernel
@@ -393,7 +448,7 @@ __global__ void __launch_bounds__(ENC_THREADS) k_post(const KParams p) {
             write_dyn(st, head, 0, e);
         }
         __syncwarp();
-        encode_tile_stage1<FMT>(st, head, flats, 1, 1, p.obs, lane, 32);
+        encode_env_stage1(st, head, flats, p.obs, lane, 32);
         __syncwarp();
         encode_env_elementwise<FMT>(st, head, flats, env, p.obs, lane, 32);
         __syncwarp();                                            // the rows are reused by the next pass
@@ -597,6 +652,8 @@ int sparc_env_create(SparcStore* store, int64_t n_envs, int traceback, int max_s
             if (shmem > 48 * 1024) {
                 cudaError_t ae = cudaFuncSetAttribute(k_env<SPARC_OBS_REFERENCE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem);
                 if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_env<SPARC_OBS_COMPACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem);
+                if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_env_host<SPARC_OBS_REFERENCE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem);
+                if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_env_host<SPARC_OBS_COMPACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem);
                 if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_encode<SPARC_OBS_REFERENCE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem);
                 if (ae == cudaSuccess) ae = cudaFuncSetAttribute(k_encode<SPARC_OBS_COMPACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem);
                 if (ae != cudaSuccess) { sparc_env_destroy(e); return fail(SPARC_E_CUDA, "dynamic shared memory: %s", cudaGetErrorString(ae)); }
@@ -648,6 +705,16 @@ int sparc_env_create(SparcStore* store, int64_t n_envs, int traceback, int max_s
     alloc((void**)&e->rew_stage, n * 4);
     alloc((void**)&e->term_stage, n);
     alloc((void**)&e->trunc_stage, n);
+    if (n <= SPARC_PACKED_MAX_ENVS) {                            // sparc_step_host on launch-bound batches (k_env_host)
+        const size_t nb = (n + 15) / 16 * 16;
+        alloc((void**)&e->done_count, sizeof(uint32_t));
+        alloc((void**)&e->packed_dev, nb);
+        if (err == cudaSuccess) err = cudaHostAlloc((void**)&e->done_host, 64, cudaHostAllocMapped);
+        if (err == cudaSuccess) { *e->done_host = 0; err = cudaHostGetDevicePointer((void**)&e->done_dev, (void*)e->done_host, 0); }
+        e->res_nb = nb;
+        if (err == cudaSuccess) err = cudaHostAlloc((void**)&e->res_host, nb * 6, cudaHostAllocMapped);
+        if (err == cudaSuccess) err = cudaHostGetDevicePointer((void**)&e->res_host_dev, (void*)e->res_host, 0);
+    }
     if (err != cudaSuccess) { sparc_env_destroy(e); return fail(SPARC_E_CUDA, "cudaMalloc: %s", cudaGetErrorString(err)); }
     k_init_state<<<(unsigned)((n + 255) / 256), 256>>>(store->d, e->s, n_envs);
     CU(cudaGetLastError());
@@ -659,8 +726,10 @@ int sparc_env_create(SparcStore* store, int64_t n_envs, int traceback, int max_s
 int sparc_env_destroy(SparcEnv* e) {
     if (!e) return SPARC_OK;
     cudaSetDevice(e->store->device);
-    void* ptrs[] = {e->s.core, e->s.vis, e->s.ep_ret, e->s.moves, e->s.stats, e->vq_count, e->vq, e->hq_count, e->hq, e->rq_count, e->rq, e->act_stage, e->rew_stage, e->term_stage, e->trunc_stage, e->info_stage, e->int_stage};
+    void* ptrs[] = {e->s.core, e->s.vis, e->s.ep_ret, e->s.moves, e->s.stats, e->vq_count, e->vq, e->hq_count, e->hq, e->rq_count, e->rq, e->act_stage, e->rew_stage, e->term_stage, e->trunc_stage, e->info_stage, e->int_stage, e->done_count, e->packed_dev};
     for (void* p : ptrs) if (p) cudaFree(p);
+    if (e->done_host) cudaFreeHost((void*)e->done_host);
+    if (e->res_host) cudaFreeHost(e->res_host);
     if (e->side) cudaStreamDestroy(e->side);
     if (e->ev_start) cudaEventDestroy(e->ev_start);
     for (cudaEvent_t ev : e->ev_dyn) if (ev) cudaEventDestroy(ev);
@@ -763,7 +832,15 @@ static int launch_env(SparcEnv* e, KParams& p, void* stream) {
     }
     {
         const size_t shmem = (size_t)(tile_head_words(p.tile) + tile_flat_words(p.st, p.tile) + tile_snap_words(p.tile)) * sizeof(uint32_t);
-        if (compact) k_env<SPARC_OBS_COMPACT><<<ntiles, CTA_THREADS, shmem, (cudaStream_t)stream>>>(p);
+        if (e->notify) {
+            p.done_flag = e->done_dev; p.done_count = e->done_count; p.done_seq = e->done_seq;
+            p.packed_out = e->packed_dev;
+            p.host_reward = reinterpret_cast<float*>(e->res_host_dev);
+            p.host_term = reinterpret_cast<uint8_t*>(e->res_host_dev + 4 * e->res_nb);
+            p.host_trunc = reinterpret_cast<uint8_t*>(e->res_host_dev + 5 * e->res_nb);
+            if (compact) k_env_host<SPARC_OBS_COMPACT><<<ntiles, CTA_THREADS, shmem, (cudaStream_t)stream>>>(p, e->pa);
+            else k_env_host<SPARC_OBS_REFERENCE><<<ntiles, CTA_THREADS, shmem, (cudaStream_t)stream>>>(p, e->pa);
+        } else if (compact) k_env<SPARC_OBS_COMPACT><<<ntiles, CTA_THREADS, shmem, (cudaStream_t)stream>>>(p);
         else k_env<SPARC_OBS_REFERENCE><<<ntiles, CTA_THREADS, shmem, (cudaStream_t)stream>>>(p);
     }
     CU(cudaGetLastError());
@@ -841,6 +918,17 @@ static void* mapped_ptr(const void* p) {
     return a.devicePointer;
 }
 
+#ifdef HOST_TIMING
+#include <time.h>
+static double g_ht[5];
+static inline double ht_now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3; }
+#define HT_T(x) const double x = ht_now()
+#define HT_ACC() do { g_ht[0] += t1 - t0; g_ht[1] += t2 - t1; g_ht[2] += t3 - t2; g_ht[3] += t4 - t3; g_ht[4] += 1; } while (0)
+extern "C" void sparc_debug_hosttiming(double* out5) { for (int k = 0; k < 5; k++) { out5[k] = g_ht[k]; g_ht[k] = 0; } }
+#else
+#define HT_T(x) ((void)0)
+#define HT_ACC() ((void)0)
+#endif
 int sparc_step_host(SparcEnv* e, const uint8_t* actions_host, float* reward_host, uint8_t* terminated_host,
                     uint8_t* truncated_host, const SparcObsOut* obs, void* stream) {
     NvtxRange nvtx_("sparc_step_host");
@@ -849,21 +937,54 @@ int sparc_step_host(SparcEnv* e, const uint8_t* actions_host, float* reward_host
     cudaStream_t s = (cudaStream_t)stream;
     const size_t n = (size_t)e->cfg.n_envs;
     SparcStepOut out; memset(&out, 0, sizeof(out));
-    static const bool zero_copy_off = getenv("SPARC_HOST_ZERO_COPY") && atoi(getenv("SPARC_HOST_ZERO_COPY")) == 0;
-    if (e->split_chunks == 0 && !zero_copy_off) {
-        // launch-bound batches (the fused k_env): with pinned buffers the kernel reads the actions from, and writes the
-        // results into, HOST memory itself (mapped over PCIe: 1 + 6 bytes per env) -- one launch and one synchronise
-        // instead of four copies around the launch (measured at 4,096 envs: 44.7 us per call with the copies, the kernel
-        // alone 11.6 us)
-        void* a = mapped_ptr(actions_host);
-        void* r = reward_host ? mapped_ptr(reward_host) : nullptr;
-        void* te = terminated_host ? mapped_ptr(terminated_host) : nullptr;
-        void* tr = truncated_host ? mapped_ptr(truncated_host) : nullptr;
-        if (a && (!reward_host || r) && (!terminated_host || te) && (!truncated_host || tr)) {
-            out.reward_dev = (float*)r; out.terminated_dev = (uint8_t*)te; out.truncated_dev = (uint8_t*)tr;
-            int rc = sparc_step(e, a, SPARC_ACT_U8, &out, obs, stream);
+    const char* ze = getenv("SPARC_HOST_ZERO_COPY");             // 0: the plain copy sequence below (A/B)
+    if (e->split_chunks == 0 && e->res_host && !(ze && atoi(ze) == 0)) {
+        // Launch-bound batches (the fused kernel): ONE launch, no copies, no synchronise.  The actions ride in the
+        // launch itself (two bits each in the kernel parameters: no PCIe read in front of the dynamics), every env's
+        // result is one byte in device memory that the last CTA to finish its dynamics expands into reward / terminated
+        // / truncated arrays in mapped host memory (one coalesced sweep) before it raises a flag there, and the host
+        // spins on the flag and copies the arrays out.  The call returns when the results are in the
+        // caller's buffers (pageable or pinned alike); the observation rewrite of this step, which stays on the device,
+        // overlaps the caller's turn-around and is ordered before anything put on `stream` later.
+        // Measured at 4,096 envs (config 2), us per call: four copies around the launch 44.7; the kernel reading and
+        // writing the caller's pinned buffers over PCIe (one sector per CTA and array) + cudaStreamSynchronize 31.5 --
+        // the same with a completion flag instead of the synchronise 30.4: the ~4,000 small PCIe transactions were
+        // the cost, not the wake-up.
+        bool ok = true;
+        HT_T(t0);
+        const size_t nw = (n + 7) / 8;
+        for (size_t k = 0; k < nw; k++) {                        // eight actions -> sixteen bits
+            uint64_t x = 0;
+            const size_t left = n - 8 * k;
+            memcpy(&x, actions_host + 8 * k, left < 8 ? left : 8);
+            if (x & 0xFCFCFCFCFCFCFCFCull) { ok = false; break; }    // an action outside 0..3 (an illegal move): plain path
+            x = (x | (x >> 6)) & 0x000F000F000F000Full;
+            x = (x | (x >> 12)) & 0x000000FF000000FFull;
+            x = (x | (x >> 24)) & 0xFFFFull;
+            uint32_t& w = e->pa.w[k >> 1];
+            w = (k & 1) ? (w | ((uint32_t)x << 16)) : (uint32_t)x;
+        }
+        if (ok) {
+            e->notify = true;
+            e->done_seq += 1;
+            HT_T(t1);
+            int rc = sparc_step(e, e->act_stage, SPARC_ACT_U8, &out, obs, stream);    // (the action pointer is not read)
+            e->notify = false;
             if (rc) return rc;
-            CU(cudaStreamSynchronize(s));
+            HT_T(t2);
+            for (uint32_t spins = 1; *e->done_host != e->done_seq; spins++) {
+                if ((spins & 0xFFFu) == 0 && cudaStreamQuery(s) != cudaErrorNotReady) break;   // finished or failed: settle below
+#if defined(__x86_64__)
+                __builtin_ia32_pause();
+#endif
+            }
+            if (*e->done_host != e->done_seq) CU(cudaStreamSynchronize(s));                     // surfaces a launch / kernel error
+            HT_T(t3);
+            if (reward_host) memcpy(reward_host, e->res_host, n * 4);
+            if (terminated_host) memcpy(terminated_host, e->res_host + 4 * e->res_nb, n);
+            if (truncated_host) memcpy(truncated_host, e->res_host + 5 * e->res_nb, n);
+            HT_T(t4);
+            HT_ACC();
             return SPARC_OK;
         }
     }

@@ -1229,6 +1229,39 @@ SPARC_HD void encode_tile_stage2(const StoreDev& st, const uint32_t* head, const
     if (obs.info_dev) expand_info(st, rz, tile_puzzle, static_cast<int64_t*>(obs.info_dev) + (size_t)env0 * st.S, nE, tid, nthr);
 }
 
+// Stage 1 for ONE env by one warp (tile = 1: k_post's rewrite of an env that began a new episode): the static words
+// of all three streams in one pass over a combined index, so that a lane has all its global loads in flight at once
+// (stream by stream, as encode_tile_stage1 does for a CTA, a lane went through up to six dependent L2 round trips:
+// delta step 38.2 -> 36.5 us), the visited words and the agent bit OR-ed in on the way.  No tails: nE = 1.
+SPARC_HD void encode_env_stage1(const StoreDev& st, const uint32_t* head, uint32_t* flats, const SparcObsOut& obs,
+                                int tid, int nthr) {
+    const uint32_t pz = head[SPARC_DYN_STRIDE];
+    const uint32_t ab = head[8];
+    const int Wb = st.W + 2, Wc = st.Wc + 2, Wz = st.nv + 2, R = Wb + Wc + Wz;
+    for (int base = tid; base < R; base += 4 * nthr) {
+        uint32_t w[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            int k = base + u * nthr;
+            w[u] = 0u;
+            if (k < Wb) {
+                if (k < st.W && obs.base_dev) w[u] = sp_ldg(st.sbits + (pz * (uint32_t)st.W + (uint32_t)k));
+            } else if ((k -= Wb) < Wc) {
+                if (k < st.Wc && obs.color_dev) w[u] = sp_ldg(st.color4 + (pz * (uint32_t)st.Wc + (uint32_t)k));
+            } else if ((k -= Wc) < st.nv && obs.info_dev) {
+                w[u] = sp_ldg(st.info_nz + (pz * (uint32_t)st.nv + (uint32_t)k));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int k = base + u * nthr;
+            if (k >= R) continue;
+            if (k < st.W) w[u] |= (k < st.nv ? head[k] : 0u) | ((int)(ab >> 5) == k ? 1u << (ab & 31) : 0u);
+            flats[k] = w[u];
+        }
+    }
+}
+
 // One env's whole observation from rows staged with tile = 1 (k_encode_list: the few envs per step that began a
 // new episode under update = SPARC_OBS_DELTA).  Element-wise stores, consecutive threads -> consecutive elements:
 // an env's streams start at 8- or 4-byte boundaries only (L*4 = 6,760 bytes on the 13x13 / 10-plane slab).
@@ -1284,6 +1317,15 @@ struct KParams {
     int fit_budget;          // nodes an inline exact-fit search may visit before the snapshot becomes a hard item (0 = no limit)
     uint32_t* rq_count;      // delta observations: number of envs that began a new episode this step (nullptr in the
     uint32_t* rq;            // fused kernel, which decides per tile); [n_envs] their indices -> k_encode_list
+    // sparc_step_host on the fused kernel: the host waits for done_flag (mapped host memory) to become done_seq instead
+    // of synchronising the stream; every CTA counts itself in done_count once its per-env results are written
+    uint32_t* done_flag;
+    uint32_t* done_count;
+    uint32_t done_seq;
+    uint8_t* packed_out;     // per env: reward code | terminated << 3 | truncated << 4 (device memory); the last CTA to
+    float* host_reward;      // finish its dynamics expands them into these arrays in mapped host memory (n rounded up
+    uint8_t* host_term;      // to 16 entries each)
+    uint8_t* host_trunc;
 };
 
 SPARC_HD long long load_action(const void* p, int dtype, long long i) {
@@ -1319,13 +1361,16 @@ SPARC_HD void obs_delta_planes(T* base, const StoreDev& st, long long i, int ox,
 enum { PA_NEW_EPISODE = 1, PA_SNAPSHOT = 2 };
 template <bool INLINE_VALIDATION = true, bool MAY_DELTA = true>
 SPARC_HD bool phase_a(const KParams& p, long long i, EnvRegs& e, uint32_t* scratch, unsigned long long* stats,
-                      int* tile_flags = nullptr, uint32_t* snap = nullptr) {
+                      int* tile_flags = nullptr, uint32_t* snap = nullptr, int packed_action = -1) {
     // tile_flags (the fused k_env): PA_NEW_EPISODE | PA_SNAPSHOT of this env.  snap: SPARC_VQ_WORDS words of the CTA's
     // shared memory; a state that needs validating is stored there instead of being validated by this thread, and
     // another warp of the CTA validates it beside the encoder (validate_snapshot).
     const StoreDev& st = p.st;
     const long long n = p.cfg.n_envs;
     load_env(e, p.sd, st, n, i);
+    // (Prefetching the header and the walk board of the puzzle a same-step autoreset would move to -- the two extra
+    // dependent L2 round trips of the 1-2 % of envs that end an episode -- changed nothing measurable: config 2 8.32 vs
+    // 8.36 us, delta 35.5-36.6 either way.)
     StepResult r;
     r.reward_code = SPARC_R_ZERO; r.terminated = 0; r.truncated = 0; r.legal_mask = 0; r.rule_flags = 0;
     bool need_legal = false, have_stats = false, new_episode = false, snapped = false;
@@ -1353,7 +1398,7 @@ SPARC_HD bool phase_a(const KParams& p, long long i, EnvRegs& e, uint32_t* scrat
         }
         need_legal = true;
     } else {                                                             // ---- live step
-        const long long a = load_action(p.actions, p.act_dtype, i);
+        const long long a = packed_action >= 0 ? (long long)packed_action : load_action(p.actions, p.act_dtype, i);
         env_step(e, st, p.sd, p.cfg, i, a, r);
         const bool done = r.terminated || r.truncated;
         if (p.cfg.validate_mode == SPARC_VALIDATE_EVERY_STEP ||
@@ -1425,6 +1470,7 @@ SPARC_HD bool phase_a(const KParams& p, long long i, EnvRegs& e, uint32_t* scrat
         }
     }
     // per-env outputs (SG.py:1238)
+    if (p.packed_out) p.packed_out[i] = (uint8_t)(r.reward_code | (r.terminated << 3) | (r.truncated << 4));
     if (p.out.reward_dev) p.out.reward_dev[i] = reward_value(r.reward_code);
     if (p.out.reward_code_dev) p.out.reward_code_dev[i] = (int8_t)r.reward_code;
     if (p.out.terminated_dev) p.out.terminated_dev[i] = (uint8_t)r.terminated;

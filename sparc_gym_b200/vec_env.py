@@ -118,6 +118,7 @@ class SparcVecEnv:
                                      self.legal_mask.data_ptr(), self.rule_flags.data_ptr(),
                                      self.step_count.data_ptr(), self.agent_xy.data_ptr())
         self.write_obs = write_obs
+        self._obs_ref, self._no_obs_ref = C.byref(self._obs_out), C.byref(self._no_obs)
 
     # -- helpers
     def _stream(self):
@@ -168,10 +169,12 @@ class SparcVecEnv:
         """End-to-end step with HOST buffers (numpy / pinned torch CPU tensors): actions are copied
         to the device, results copied back, stream synchronised (sparc_step_host)."""
         ptr = lambda a: a.data_ptr() if isinstance(a, torch.Tensor) else a.ctypes.data
-        with torch.cuda.device(self.device):
-            abi.check(self.lib.sparc_step_host(self.handle, ptr(actions_host), ptr(reward_host), ptr(terminated_host),
-                                               ptr(truncated_host),
-                                               C.byref(self._obs_out if self.write_obs else self._no_obs), self._stream()))
+        # (no torch.cuda.device() context here: the library selects the store's device itself, and on a launch-bound
+        # batch the context manager alone was a tenth of the call)
+        rc = self.lib.sparc_step_host(self.handle, ptr(actions_host), ptr(reward_host), ptr(terminated_host), ptr(truncated_host),
+                                      self._obs_ref if self.write_obs else self._no_obs_ref, self._stream())
+        if rc:
+            abi.check(rc)
 
     # -- host-record calls (the single-env drop-in): one launch sequence, ONE device->host copy, no torch ops
     def _info_record(self):

@@ -105,7 +105,7 @@ int emu_launch(const SparcStoreDesc* desc, uint32_t* core, uint32_t* vis, int32_
             load_env(e, p.sd, st, n_envs, env);
             head[SPARC_DYN_STRIDE] = e.puzzle;
             write_dyn(st, head, 0, e);
-            for (int tid = 0; tid < nthr; tid++) encode_tile_stage1(st, head, flats, 1, 1, p.obs, tid, nthr);
+            for (int tid = 0; tid < nthr; tid++) encode_env_stage1(st, head, flats, p.obs, tid, nthr);
             for (int tid = 0; tid < nthr; tid++) {
                 if (p.obs.format == SPARC_OBS_COMPACT) encode_env_elementwise<SPARC_OBS_COMPACT>(st, head, flats, env, p.obs, tid, nthr);
                 else encode_env_elementwise<SPARC_OBS_REFERENCE>(st, head, flats, env, p.obs, tid, nthr);
