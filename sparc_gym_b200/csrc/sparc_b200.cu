@@ -93,6 +93,8 @@ struct SparcEnv {
     uint32_t done_seq;
     bool notify;             // this launch is k_env_host: packed actions in, packed results + done flag out
     uint8_t* packed_dev;     // [n_envs rounded up to 16] per-env result bytes
+    char* info_host;         // mapped host memory: the record of sparc_*_info_host (k_info; allocated on first use)
+    char* info_host_dev;
     char* res_host;          // mapped host memory: reward f32[nb] | terminated u8[nb] | truncated u8[nb], nb = n_envs rounded up to 16
     char* res_host_dev;
     size_t res_nb;
@@ -182,8 +184,9 @@ __device__ __forceinline__ void k_env_body(const KParams& p, const uint32_t* pac
     if (tid < nE) {
         // a state that needs validating is left in shared memory: warp 3 validates it while warps 0-2 encode (inline,
         // the other 127 threads of the CTA waited at the barrier for it: 10.1 -> 8.8 us per step on config 2)
-        int fl = 0, pk = -1;
-        if (packed_actions) { const long long i = env0 + tid; pk = (int)(packed_actions[i >> 4] >> ((i & 15) * 2)) & 3; }
+        int fl = 0;
+        long long pk = SPARC_NO_ARG;
+        if (packed_actions) { const long long i = env0 + tid; pk = (long long)((packed_actions[i >> 4] >> ((i & 15) * 2)) & 3u); }
         have_stats = phase_a<false, true>(p, env0 + tid, e, head + tid * SPARC_DYN_STRIDE, my_stats, &fl, snaps + tid * SPARC_VQ_WORDS, pk);
         tflags[tid] = (uint32_t)fl;
         head[p.tile * SPARC_DYN_STRIDE + tid] = e.puzzle;
@@ -485,6 +488,76 @@ __global__ void __launch_bounds__(CTA_THREADS) k_validate(const StoreDev st, con
     if (flags) flags[i] = (uint16_t)(f | SPARC_RULE_VALID);
 }
 
+// sparc_step_info_host / sparc_reset_info_host for a handful of envs (the single-env Gymnasium drop-in): ONE launch does
+// everything the call returns.  CTA = env: thread 0 steps (or resets) it -- the action / puzzle index came with the launch
+// -- and validates the state it is left in, region map and per-region verdicts into shared memory; the CTA then writes
+// the env's part of the host record (struct of arrays, see include/sparc_b200.h) with coalesced stores over PCIe, the
+// last CTA raises the completion flag the host spins on, and the observation is rewritten after that.
+// (As three launches -- k_env and k_validate writing into mapped host memory byte by byte, then a stream synchronise --
+// one step of one env cost 37 us; tools/hostcall_probe.py.)
+#define SPARC_INFO_MAX_ENVS 16
+struct SmallInts { long long v[SPARC_INFO_MAX_ENVS]; };
+template <int FMT>
+__global__ void __launch_bounds__(CTA_THREADS) k_info(const KParams p, const SmallInts args, char* rec) {
+    const StoreDev& st = p.st;
+    const int tid = threadIdx.x;
+    const long long i = blockIdx.x, n = p.cfg.n_envs;
+    uint32_t* head = smem;                                       // tile = 1: dyn row + puzzle id | rows | this env's record
+    uint32_t* flats = smem + tile_head_words(1);
+    int8_t* rfit = reinterpret_cast<int8_t*>(flats + tile_flat_words(st, 1));
+    int8_t* rmap = rfit + SPARC_MAX_REGIONS;
+    __shared__ int s_small[8];
+    __shared__ uint32_t s_snap[SPARC_VQ_WORDS];
+    for (int k = tid; k < SPARC_MAX_REGIONS + st.S; k += CTA_THREADS) rfit[k] = k < SPARC_MAX_REGIONS ? (int8_t)SPARC_FIT_NONE : (int8_t)-1;
+    __syncthreads();
+    unsigned long long my_stats[SPARC_N_STATS];
+    bool have_stats = false;
+    if (tid == 0) {
+        EnvRegs e;
+        StepResult r;
+        int fl = 0;
+        uint32_t* snap = s_snap;
+        have_stats = phase_a<false, true>(p, i, e, head, my_stats, &fl, snap, args.v[i], &r);
+        if ((fl & PA_SNAPSHOT) && (validate_snapshot(p, snap) & (int)snap[3]))      // validate = terminal / every_step: the statistic
+            atomicAdd(p.sd.stats + (size_t)(blockIdx.x % SPARC_STAT_ROWS) * SPARC_N_STATS + SPARC_STAT_RULES_PASS, 1ull);
+        uint32_t vd[9];
+#pragma unroll
+        for (int k = 0; k < 8; k++) vd[k] = e.v[k];
+        vd[8] = 0;
+        const int f = validate_env(st, e.puzzle, vd, e.x, e.y, rmap, rfit) | SPARC_RULE_VALID;      // SG.py:1011: the state as it is now
+        s_small[0] = (int)e.step; s_small[1] = f; s_small[2] = e.x | (e.y << 8);
+        s_small[3] = (r.reward_code & 0xff) | (r.terminated << 8) | (r.truncated << 16) | (r.legal_mask << 24);
+        head[SPARC_DYN_STRIDE] = e.puzzle;
+        write_dyn(st, head, 0, e);
+    }
+    if (p.mode == 0 && tid < 32) reduce_stats(p, have_stats, my_stats);
+    __syncthreads();
+    if (tid == 0) {                                              // int32 step[n] | uint16 flags[n] | uint8 agent_xy[n][2] | int8 reward_code[n] |
+        reinterpret_cast<int32_t*>(rec)[i] = s_small[0];        // uint8 terminated[n] | uint8 truncated[n] | uint8 legal_mask[n]
+        reinterpret_cast<uint16_t*>(rec + 4 * n)[i] = (uint16_t)s_small[1];
+        reinterpret_cast<uint16_t*>(rec + 6 * n)[i] = (uint16_t)s_small[2];
+        rec[8 * n + i] = (char)(s_small[3] & 0xff); rec[9 * n + i] = (char)((s_small[3] >> 8) & 0xff);
+        rec[10 * n + i] = (char)((s_small[3] >> 16) & 0xff); rec[11 * n + i] = (char)((s_small[3] >> 24) & 0xff);
+    }
+    int8_t* fit_out = reinterpret_cast<int8_t*>(rec + 12 * n) + (size_t)i * SPARC_MAX_REGIONS;    // | int8 region_fit[n][SPARC_MAX_REGIONS]
+    int8_t* map_out = reinterpret_cast<int8_t*>(rec + (12 + SPARC_MAX_REGIONS) * n) + (size_t)i * st.S;   // | int8 region_map[n][S]
+    for (int k = tid; k < SPARC_MAX_REGIONS; k += CTA_THREADS) fit_out[k] = rfit[k];
+    for (int k = tid; k < st.S; k += CTA_THREADS) map_out[k] = rmap[k];
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence_system();
+        if (atomicAdd(p.done_count, 1u) == gridDim.x - 1) {
+            *p.done_count = 0;
+            __threadfence_system();
+            *reinterpret_cast<volatile uint32_t*>(p.done_flag) = p.done_seq;
+        }
+    }
+    if (!p.obs.base_dev && !p.obs.color_dev && !p.obs.info_dev) return;
+    encode_env_stage1(st, head, flats, p.obs, tid, CTA_THREADS);
+    __syncthreads();
+    encode_env_elementwise<FMT>(st, head, flats, i, p.obs, tid, CTA_THREADS);
+}
+
 // a fresh env is a clean reset on puzzle i mod pool: stepping, encoding or validating before the first sparc_reset
 // works on a state a puzzle can produce (start node visited, agent on the start)
 __global__ void k_init_state(StoreDev st, StateDev sd, long long n) {
@@ -730,6 +803,7 @@ int sparc_env_destroy(SparcEnv* e) {
     for (void* p : ptrs) if (p) cudaFree(p);
     if (e->done_host) cudaFreeHost((void*)e->done_host);
     if (e->res_host) cudaFreeHost(e->res_host);
+    if (e->info_host) cudaFreeHost(e->info_host);
     if (e->side) cudaStreamDestroy(e->side);
     if (e->ev_start) cudaEventDestroy(e->ev_start);
     for (cudaEvent_t ev : e->ev_dyn) if (ev) cudaEventDestroy(ev);
@@ -1017,8 +1091,39 @@ static int info_call(SparcEnv* e, bool reset, const int32_t* ints_host, void* re
     CU(cudaSetDevice(e->store->device));
     cudaStream_t s = (cudaStream_t)stream;
     const size_t n = (size_t)e->cfg.n_envs, bytes = (size_t)sparc_info_record_bytes(e);
-    // pinned host buffers: the kernels read the actions from and write the record into host memory themselves (a
-    // few hundred bytes per env over PCIe) -- no copies around the launches, which is most of what one env's step costs
+    if (n <= SPARC_INFO_MAX_ENVS && e->done_host && obs &&
+        (obs->format == SPARC_OBS_REFERENCE || obs->format == SPARC_OBS_COMPACT)) {
+        // a handful of envs (the single-env drop-in): one launch of k_info, the arguments in the launch, the record
+        // written into mapped host memory by the kernel, a completion flag instead of a synchronise (see k_info)
+        if (!e->info_host) {
+            CU(cudaHostAlloc((void**)&e->info_host, bytes, cudaHostAllocMapped));
+            CU(cudaHostGetDevicePointer((void**)&e->info_host_dev, (void*)e->info_host, 0));
+        }
+        KParams p; memset(&p, 0, sizeof(p));
+        p.st = e->store->d; p.sd = e->s; p.cfg = e->cfg; p.tile = 1;
+        p.mode = reset ? 1 : 0;
+        p.obs = *obs; p.obs.update = SPARC_OBS_REWRITE;
+        SmallInts args;
+        for (size_t k = 0; k < n; k++) args.v[k] = ints_host ? (long long)ints_host[k] : SPARC_NO_ARG;
+        e->done_seq += 1;
+        p.done_flag = e->done_dev; p.done_count = e->done_count; p.done_seq = e->done_seq;
+        const size_t shmem = (size_t)(tile_head_words(1) + tile_flat_words(p.st, 1)) * sizeof(uint32_t) + SPARC_MAX_REGIONS + (size_t)p.st.S;
+        if (obs->format == SPARC_OBS_COMPACT) k_info<SPARC_OBS_COMPACT><<<(unsigned)n, CTA_THREADS, shmem, s>>>(p, args, e->info_host_dev);
+        else k_info<SPARC_OBS_REFERENCE><<<(unsigned)n, CTA_THREADS, shmem, s>>>(p, args, e->info_host_dev);
+        CU(cudaGetLastError());
+        e->launches++;
+        for (uint32_t spins = 1; *e->done_host != e->done_seq; spins++) {
+            if ((spins & 0xFFFu) == 0 && cudaStreamQuery(s) != cudaErrorNotReady) break;       // finished or failed: settle below
+#if defined(__x86_64__)
+            __builtin_ia32_pause();
+#endif
+        }
+        if (*e->done_host != e->done_seq) CU(cudaStreamSynchronize(s));                         // surfaces a launch / kernel error
+        memcpy(record_host, e->info_host, bytes);
+        return SPARC_OK;
+    }
+    // more envs: pinned host buffers are read and written by the kernels themselves (a few hundred bytes per env over
+    // PCIe), pageable ones go through device staging
     char* b = (char*)mapped_ptr(record_host);
     const int32_t* ints = ints_host ? (const int32_t*)mapped_ptr(ints_host) : nullptr;
     const bool direct = b && (!ints_host || ints) && e->split_chunks == 0;

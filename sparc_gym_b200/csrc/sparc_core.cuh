@@ -1359,9 +1359,14 @@ SPARC_HD void obs_delta_planes(T* base, const StoreDev& st, long long i, int ox,
 // MAY_DELTA = false compiles the in-place observation update out (k_dyn of the full-rewrite step: 62 registers
 // instead of 66, i.e. 8 instead of 7 resident CTAs per SM).
 enum { PA_NEW_EPISODE = 1, PA_SNAPSHOT = 2 };
+#define SPARC_NO_ARG (-0x7fffffffffffffffll - 1)
 template <bool INLINE_VALIDATION = true, bool MAY_DELTA = true>
 SPARC_HD bool phase_a(const KParams& p, long long i, EnvRegs& e, uint32_t* scratch, unsigned long long* stats,
-                      int* tile_flags = nullptr, uint32_t* snap = nullptr, int packed_action = -1) {
+                      int* tile_flags = nullptr, uint32_t* snap = nullptr, long long arg = SPARC_NO_ARG,
+                      StepResult* result = nullptr) {
+    // arg: this env's action (step) or puzzle index (reset) when it came with the launch instead of through
+    // p.actions / p.reset_idx (the host-buffer calls on launch-bound batches).  result: the step's outcome for a
+    // caller that writes the per-env outputs itself.
     // tile_flags (the fused k_env): PA_NEW_EPISODE | PA_SNAPSHOT of this env.  snap: SPARC_VQ_WORDS words of the CTA's
     // shared memory; a state that needs validating is stored there instead of being validated by this thread, and
     // another warp of the CTA validates it beside the encoder (validate_snapshot).
@@ -1379,7 +1384,7 @@ SPARC_HD bool phase_a(const KParams& p, long long i, EnvRegs& e, uint32_t* scrat
         const bool sel = p.reset_mask ? p.reset_mask[i] != 0 : true;
         if (sel) {
             // indices are taken modulo the pool, Python style (-1 = the last puzzle); host wrappers range-check first
-            int pzi = p.reset_idx ? p.reset_idx[i] % st.n_puzzles : (int)e.puzzle;
+            int pzi = arg != SPARC_NO_ARG ? (int)(arg % st.n_puzzles) : p.reset_idx ? p.reset_idx[i] % st.n_puzzles : (int)e.puzzle;
             if (pzi < 0) pzi += st.n_puzzles;
             const uint32_t pz = (uint32_t)pzi;
             env_reset(e, st, pz);
@@ -1398,7 +1403,7 @@ SPARC_HD bool phase_a(const KParams& p, long long i, EnvRegs& e, uint32_t* scrat
         }
         need_legal = true;
     } else {                                                             // ---- live step
-        const long long a = packed_action >= 0 ? (long long)packed_action : load_action(p.actions, p.act_dtype, i);
+        const long long a = arg != SPARC_NO_ARG ? arg : load_action(p.actions, p.act_dtype, i);
         env_step(e, st, p.sd, p.cfg, i, a, r);
         const bool done = r.terminated || r.truncated;
         if (p.cfg.validate_mode == SPARC_VALIDATE_EVERY_STEP ||
@@ -1469,6 +1474,7 @@ SPARC_HD bool phase_a(const KParams& p, long long i, EnvRegs& e, uint32_t* scrat
             else obs_delta_planes(static_cast<int32_t*>(p.obs.base_dev), st, i, ox, oy, e);
         }
     }
+    if (result) *result = r;
     // per-env outputs (SG.py:1238)
     if (p.packed_out) p.packed_out[i] = (uint8_t)(r.reward_code | (r.terminated << 3) | (r.truncated << 4));
     if (p.out.reward_dev) p.out.reward_dev[i] = reward_value(r.reward_code);

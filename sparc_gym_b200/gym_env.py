@@ -142,41 +142,79 @@ class _Details:
                                   "colors": colors[r]} for r in range(len(area))}
         return status
 
-    def _region_symbols(self):
-        """Per region id: area, symbols[layer] = [(x, y), ...] and colour counts (SG.py:456-482), from the
-        device's region map and the puzzle's planes."""
-        rmap = self._region_map
-        n = int(rmap.max()) + 1
-        area = [int((rmap == r).sum()) for r in range(n)]
-        symbols = [dict() for _ in range(n)]
-        colors = [dict() for _ in range(n)]
-        for layer, arr in self.obs_array.items():
+    def _static_facts(self):
+        """Everything `rule_status` needs that does not change while a puzzle is loaded, gathered once per load (the
+        containers are fresh per load, SG.py:149-151): symbol cells in the order SG.py:456-482 meets them, dots,
+        triangles, shape instances.  Looking these up in the numpy planes every step was most of the step's host time."""
+        st = getattr(self, "_static", None)
+        if st is not None and st["planes"] is self.obs_array:
+            return st
+        planes, color, info = self.obs_array, self.color_array, self.additional_info
+        cells = []
+        for layer, arr in planes.items():
             if layer in FIXED_KEYS:
                 continue
             for x, y in zip(*np.where(arr == 1)):
-                rid = int(rmap[x, y])
-                if rid == -1:
-                    continue
-                symbols[rid].setdefault(layer, []).append((int(x), int(y)))
-                c = self.color_array[x, y]
-                if c:
-                    colors[rid][c] = colors[rid].get(c, 0) + 1
+                cells.append((layer, int(x), int(y), color[x, y]))
+        st = {"planes": planes, "cells": cells}
+        st["dots"] = [(int(x), int(y)) for x, y in zip(*np.where(planes["dot"] == 1))] if "dot" in planes else None
+        sx, sy = self.start_location                          # the only path node that can sit on a gap (SG.py:508-519)
+        st["gap_violations"] = [(int(sx), int(sy))] if planes["gaps"][sx, sy] == 1 else []
+        st["triangles"] = None
+        if "triangle" in planes:                                                        # SG.py:617-646
+            tri = planes["triangle"]
+            st["triangles"] = [(x, y, int(info[x, y])) for x in range(1, self.x_size - 1) for y in range(1, self.y_size - 1)
+                               if tri[x, y] == 1 and int(info[x, y]) > 0]
+        inst = []                                                                       # SG.py:648-736
+        if isinstance(self.polyshapes, dict):
+            for x in range(self.x_size):
+                for y in range(self.y_size):
+                    v = info[x, y]
+                    if v != 0 and f"{v}" in self.polyshapes:
+                        kind = "poly" if planes["poly"][x, y] == 1 else "ylop"
+                        inst.append((x, y, kind, int(np.array(self.polyshapes[f"{v}"]).sum())))
+        st["instances"] = inst
+        st["has_instances"] = self._has_instances()
+        st["target"] = self._target_location.tolist()
+        self._static = st
+        return st
+
+    def _region_symbols(self):
+        """Per region id: area, symbols[layer] = [(x, y), ...] and colour counts (SG.py:456-482), from the
+        device's region map and the puzzle's symbol cells."""
+        rm = self._region_map.tolist()
+        self._rm_rows = rm
+        area = np.bincount(self._region_map.ravel().astype(np.int64) + 1).tolist()[1:]    # region -1 = the path itself
+        n = len(area)
+        symbols = [dict() for _ in range(n)]
+        colors = [dict() for _ in range(n)]
+        for layer, x, y, c in self._static_facts()["cells"]:
+            rid = rm[x][y]
+            if rid == -1:
+                continue
+            sym = symbols[rid]
+            if layer in sym:
+                sym[layer].append((x, y))
+            else:
+                sym[layer] = [(x, y)]
+            if c:
+                col = colors[rid]
+                col[c] = col.get(c, 0) + 1
         return area, symbols, colors
 
     def _rule_details(self, area, symbols):
         """The `detail` payloads of SG.py:488-710.  Every fact comes from the device (flags, region map,
         per-region poly/ylop verdicts, visited plane); this only arranges them in the reference's containers."""
-        planes, color, info = self.obs_array, self.color_array, self.additional_info
+        planes, color = self.obs_array, self.color_array
+        st, rm = self._static_facts(), self._rm_rows
+        vis = planes["visited"].tolist()
         d = {}
         d["reached_target"] = {"agent_loc": self._agent_location.tolist(),              # SG.py:493-496
-                               "target_loc": self._target_location.tolist()}
+                               "target_loc": list(st["target"])}
         d["path_not_crossing"] = {"duplicates": {}}          # path nodes are distinct (clean resets, legal moves)
-        sx, sy = self.start_location                          # the only path node that can sit on a gap (SG.py:508-519)
-        d["no_gap_violations"] = {"violations": [(int(sx), int(sy))] if planes["gaps"][sx, sy] == 1 else []}
-        if "dot" in planes:                                                             # SG.py:521-532
-            dots = planes["dot"] == 1
-            d["all_dots_collected"] = {"total": int(dots.sum()),
-                                       "collected": int((dots & (planes["visited"] == 1)).sum())}
+        d["no_gap_violations"] = {"violations": list(st["gap_violations"])}
+        if st["dots"] is not None:                                                      # SG.py:521-532
+            d["all_dots_collected"] = {"total": len(st["dots"]), "collected": sum(1 for (x, y) in st["dots"] if vis[x][y] == 1)}
         else:
             d["all_dots_collected"] = {"total": 0, "collected": 0}
         if "square" in planes:                                                          # SG.py:534-552
@@ -223,28 +261,19 @@ class _Details:
             d["star_pairing_exact"] = {"violations": violations, "per_region": per_region}
         else:
             d["star_pairing_exact"] = {"regions": []}
-        if "triangle" in planes:                                                        # SG.py:617-646
-            tri, vis, mism = planes["triangle"], planes["visited"], []
-            for x in range(1, self.x_size - 1):
-                for y in range(1, self.y_size - 1):
-                    if tri[x, y] == 1 and int(info[x, y]) > 0:
-                        touches = int(vis[x + 1, y] + vis[x - 1, y] + vis[x, y - 1] + vis[x, y + 1])
-                        if touches != int(info[x, y]):
-                            mism.append({"x": x, "y": y, "required": int(info[x, y]), "touches": touches})
-            d["triangles_edge_count"] = {"mismatches": mism}
-        else:
-            d["triangles_edge_count"] = {"mismatches": []}
+        mism = []
+        if st["triangles"] is not None:                                                 # SG.py:617-646
+            for x, y, need in st["triangles"]:
+                touches = vis[x + 1][y] + vis[x - 1][y] + vis[x][y - 1] + vis[x][y + 1]
+                if touches != need:
+                    mism.append({"x": x, "y": y, "required": need, "touches": touches})
+        d["triangles_edge_count"] = {"mismatches": mism}
         by_region = {}                                                                  # SG.py:648-736
-        if isinstance(self.polyshapes, dict):
-            for x in range(self.x_size):
-                for y in range(self.y_size):
-                    v = info[x, y]
-                    if v != 0 and f"{v}" in self.polyshapes:
-                        rid = int(self._region_map[x, y])
-                        if rid != -1:
-                            kind = "poly" if planes["poly"][x, y] == 1 else "ylop"
-                            by_region.setdefault(rid, []).append((kind, int(np.array(self.polyshapes[f"{v}"]).sum())))
-        if not by_region and not self._has_instances():
+        for x, y, kind, shape_area in st["instances"]:
+            rid = rm[x][y]
+            if rid != -1:
+                by_region.setdefault(rid, []).append((kind, shape_area))
+        if not by_region and not st["has_instances"]:
             d["poly_ylop_area"] = {"regions": []}
         else:
             det = []
@@ -287,6 +316,9 @@ class _Snap(_Details):
         self.start_location, self.x_size, self.y_size = env.start_location, env.x_size, env.y_size
         self.polyshapes, self._flags = env.polyshapes, env._flags
         self._region_map, self._region_fit = env._region_map, env._region_fit
+        st = dict(env._static_facts())
+        st["planes"] = self.obs_array                      # (this snapshot's own dict; same static planes)
+        self._static = st
 
 
 class SPaRC_Gym(_Details, _Env):
