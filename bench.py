@@ -476,7 +476,9 @@ def main():
                "h2d_bytes_per_step": n_env * world, "d2h_bytes_per_step": n_env * world * 6,
                "wall_ms_per_step": round(wall_ms / K, 4),
                "api": "SparcVecEnv.step_host -> sparc_step_host (pinned host actions in; reward f32 + terminated u8 + "
-                      "truncated u8 out; observation tensors stay on the device for the policy)"}
+                      "truncated u8 out; observation tensors stay on the device for the policy; the call returns when the "
+                      "results are in the host buffers, the observation rewrite of that step is stream-ordered behind it "
+                      "and overlaps the caller's turn-around; the timed region ends with a full synchronise)"}
 
     # ---- the statistics collective inside the loop: K steps from Python with and without stats_async
     stats_coll = None

@@ -67,7 +67,7 @@ struct SparcEnv {
     cudaStream_t side;       // high-priority stream of k_dyn (multi-chunk) / k_val
     cudaEvent_t ev_start, ev_dyn[16], ev_val;
     cudaStream_t copy_stream;   // sparc_step_host: result copies run beside k_encode
-    cudaEvent_t ev_dyn_done, ev_copy;
+    cudaEvent_t ev_dyn_done, ev_copy, ev_act;
     struct { float* reward; uint8_t* term; uint8_t* trunc; bool active; } hostcopy;
     uint32_t* vq_count;      // deferred-validation queue (split path, validate = terminal)
     uint32_t* vq;
@@ -742,6 +742,7 @@ int sparc_env_create(SparcStore* store, int64_t n_envs, int traceback, int max_s
             if (se == cudaSuccess) se = cudaStreamCreateWithPriority(&e->copy_stream, cudaStreamNonBlocking, hi_p);
             if (se == cudaSuccess) se = cudaEventCreateWithFlags(&e->ev_dyn_done, cudaEventDisableTiming);
             if (se == cudaSuccess) se = cudaEventCreateWithFlags(&e->ev_copy, cudaEventDisableTiming);
+            if (se == cudaSuccess) se = cudaEventCreateWithFlags(&e->ev_act, cudaEventDisableTiming);
             const char* de = getenv("SPARC_DEFER_VALIDATION");
             if (se == cudaSuccess && !(de && atoi(de) == 0)) {
                 se = cudaMalloc((void**)&e->vq_count, 4 * sizeof(uint32_t));   // see k_val
@@ -811,6 +812,7 @@ int sparc_env_destroy(SparcEnv* e) {
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->ev_dyn_done) cudaEventDestroy(e->ev_dyn_done);
     if (e->ev_copy) cudaEventDestroy(e->ev_copy);
+    if (e->ev_act) cudaEventDestroy(e->ev_act);
     delete e;
     return SPARC_OK;
 }
@@ -1062,10 +1064,22 @@ int sparc_step_host(SparcEnv* e, const uint8_t* actions_host, float* reward_host
             return SPARC_OK;
         }
     }
-    CU(cudaMemcpyAsync(e->act_stage, actions_host, n, cudaMemcpyHostToDevice, s));
     out.reward_dev = e->rew_stage; out.terminated_dev = e->term_stage; out.truncated_dev = e->trunc_stage;
-    // big batches: the result copies are issued right behind k_dyn on a side stream and overlap k_encode
+    // Big batches: the result copies are issued right behind k_dyn on a side stream and overlap k_encode, and the call
+    // returns when THEY are done -- not when the observation rewrite is, which stays on the device and is ordered before
+    // anything put on `stream` later.  The caller's turn-around (and the next call's action upload, on the same side
+    // stream) then overlaps the encoder instead of following it: the GPU never waits for the host.
+    // SPARC_HOST_EARLY=0: synchronise the stream as before (A/B).
     const bool overlap = e->split_chunks == 1 && e->copy_stream;
+    const char* ee = getenv("SPARC_HOST_EARLY");
+    const bool early = overlap && !(ee && atoi(ee) == 0);
+    if (early) {
+        CU(cudaMemcpyAsync(e->act_stage, actions_host, n, cudaMemcpyHostToDevice, e->copy_stream));
+        CU(cudaEventRecord(e->ev_act, e->copy_stream));
+        CU(cudaStreamWaitEvent(s, e->ev_act, 0));
+    } else {
+        CU(cudaMemcpyAsync(e->act_stage, actions_host, n, cudaMemcpyHostToDevice, s));
+    }
     if (overlap) { e->hostcopy.reward = reward_host; e->hostcopy.term = terminated_host; e->hostcopy.trunc = truncated_host; e->hostcopy.active = true; }
     int rc = sparc_step(e, e->act_stage, SPARC_ACT_U8, &out, obs, stream);
     e->hostcopy.active = false;
@@ -1075,7 +1089,8 @@ int sparc_step_host(SparcEnv* e, const uint8_t* actions_host, float* reward_host
         if (terminated_host) CU(cudaMemcpyAsync(terminated_host, e->term_stage, n, cudaMemcpyDeviceToHost, s));
         if (truncated_host) CU(cudaMemcpyAsync(truncated_host, e->trunc_stage, n, cudaMemcpyDeviceToHost, s));
     }
-    CU(cudaStreamSynchronize(s));
+    if (early) CU(cudaEventSynchronize(e->ev_copy));
+    else CU(cudaStreamSynchronize(s));
     return SPARC_OK;
 }
 
