@@ -458,17 +458,19 @@ def main():
     # ---- end to end: host action buffer -> H2D -> step -> D2H reward/terminated/truncated, every step
     e2e = None
     if not args.no_e2e:
-        a_host = torch.randint(0, 4, (n_env,), dtype=torch.uint8).pin_memory()
+        # fresh uniform actions every step, as in the device-resident loop (one vector repeated K times walks every env
+        # into a wall within a few steps: no episode ends, nothing to validate or reset -- an easier workload)
+        a_host = torch.randint(0, 4, (K + 3, n_env), dtype=torch.uint8, generator=torch.Generator().manual_seed(4321 + rank)).pin_memory()
         r_host = torch.empty(n_env, dtype=torch.float32).pin_memory()
         te_host = torch.empty(n_env, dtype=torch.uint8).pin_memory()
         tr_host = torch.empty(n_env, dtype=torch.uint8).pin_memory()
-        for _ in range(3):
-            env.step_host(a_host, r_host, te_host, tr_host)
+        for t in range(3):
+            env.step_host(a_host[K + t], r_host, te_host, tr_host)
         barrier()
         t0 = time.perf_counter()
         ev0.record()
-        for _ in range(K):
-            env.step_host(a_host, r_host, te_host, tr_host)
+        for t in range(K):
+            env.step_host(a_host[t], r_host, te_host, tr_host)
         ev1.record()
         barrier()
         wall_ms = (time.perf_counter() - t0) * 1e3

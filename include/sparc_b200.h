@@ -240,9 +240,14 @@ int sparc_validate(SparcEnv* env, const uint8_t* mask_dev, uint16_t* flags_dev,
  * to out_dev (device) on `stream`; clear != 0 zeroes the accumulators afterwards. */
 int sparc_stats(SparcEnv* env, int64_t* out_dev, int clear, void* stream);
 
-/* HOST-buffer step, the end-to-end call: copies `actions_host` (uint8[n_envs]) to the device,
- * steps, and copies reward / terminated / truncated back into the host arrays (any may be NULL),
- * then synchronises `stream`.  Observations stay on the device in `obs`. */
+/* HOST-buffer step, the end-to-end call: takes `actions_host` (uint8[n_envs], pageable or pinned), steps, and
+ * fills the host arrays reward / terminated / truncated (any may be NULL).  Observations stay on the device in
+ * `obs`.  The call returns when the RESULTS are in the host arrays: the observation rewrite of this step may still
+ * be running then; it is ordered before anything put on `stream` later (kernels, copies, a synchronise), so a
+ * device-side consumer needs no extra care and a host-side one synchronises `stream` first.
+ * Launch-bound batches (<= 8,192 envs) are one launch with the actions in the kernel parameters and a completion
+ * flag in mapped host memory; bigger ones upload / download on a side stream beside the encoder.
+ * SPARC_HOST_EARLY=0 / SPARC_HOST_ZERO_COPY=0 in the environment restore the plain copy + synchronise sequences. */
 int sparc_step_host(SparcEnv* env, const uint8_t* actions_host, float* reward_host,
                     uint8_t* terminated_host, uint8_t* truncated_host,
                     const SparcObsOut* obs, void* stream);
@@ -250,8 +255,9 @@ int sparc_step_host(SparcEnv* env, const uint8_t* actions_host, float* reward_ho
 /* HOST-record step / reset: what the single-env Gymnasium drop-in needs after every call, in ONE device->host copy
  * (the reference's step() returns info with legal actions, step counter, agent location and the rule status of the
  * CURRENT state, SG.py:994-1022): steps (or resets) all envs, validates every env's current state (flags, region
- * map, per-region poly/ylop verdicts: sparc_validate), copies the record below into `record_host` and synchronises
- * `stream`.  actions_host / puzzle_idx_host: int32[n_envs] in host memory (puzzle_idx_host may be NULL = keep).
+ * map, per-region poly/ylop verdicts: sparc_validate) and fills `record_host` with the record below; like
+ * sparc_step_host it returns when the record is there (up to 16 envs: ONE launch, arguments in the kernel parameters,
+ * completion flag in mapped host memory; more: launches + copy + synchronise).  actions_host / puzzle_idx_host: int32[n_envs] in host memory (puzzle_idx_host may be NULL = keep).
  * Record, struct of arrays over the n envs, sparc_info_record_bytes(env) bytes:
  *   int32 step[n] | uint16 flags[n] (SPARC_RULE_* | SPARC_RULE_VALID) | uint8 agent_xy[n][2] | int8 reward_code[n] |
  *   uint8 terminated[n] | uint8 truncated[n] | uint8 legal_mask[n] | int8 region_fit[n][SPARC_MAX_REGIONS] |

@@ -145,16 +145,58 @@ def test_step_host_matches_device_step():
         keep = torch.empty(n, dtype=torch.uint8).pin_memory()
         for t in range(30):
             act = torch.from_numpy(rng.integers(0, 4, n).astype(np.uint8))
+            if t % 9 == 4:
+                act[t] = 9                                      # an illegal move (SG.py:1137): not expressible in two bits
             if t < 10:
-                a.step_host(act.pin_memory(), r, te, tr)       # a new host buffer every call (small batches: a new graph each time)
+                a.step_host(act.pin_memory(), r, te, tr)       # a new host buffer every call
             elif t < 25:
                 keep.copy_(act)
-                a.step_host(keep, r, te, tr)                   # the same buffers: the captured graph is replayed
+                a.step_host(keep, r, te, tr)                   # the same buffers
             else:
                 a.step_host(act.numpy(), r, te, tr)            # pageable memory: the plain call sequence
             ob, rb, tb, ub, _ = b.step(act.cuda())
             assert torch.equal(r, rb.cpu()) and torch.equal(te, tb.cpu()) and torch.equal(tr, ub.cpu()), (n, t)
             assert all(torch.equal(a.obs[k], ob[k]) for k in ob)
+
+
+@pytest.mark.parametrize("n", [1, 5, 16, 40])
+@pytest.mark.parametrize("mode,validate", [("continue", "never"), ("same_step", "terminal")])
+def test_info_host_calls_match_step_plus_validate(n, mode, validate):
+    """sparc_step_info_host / sparc_reset_info_host (up to 16 envs: ONE launch of k_info with the arguments in the kernel
+    parameters and a completion flag; more: the launch + copy sequence) return exactly what a device step followed by
+    sparc_validate of the new state returns -- every field of the host record, the observation, the statistics; with
+    illegal actions (-1, 7), resets on chosen puzzles and both validation settings."""
+    rows = gen_pool(6, [(3, 3), (4, 4), (6, 6)], RULES_FULL, seed0=300)
+    kw = dict(traceback=True, max_steps=18, autoreset_mode=mode, validate=validate)
+    a, b = make_env(rows, n, **kw), make_env(rows, n, **kw)
+    rng = np.random.default_rng(n)
+    idx = rng.integers(0, len(rows), n).astype(np.int32)
+
+    def check(rec, t):
+        flags, rmap, rfit = b.validate(region_map=True, region_fit=True)
+        torch.cuda.synchronize()
+        assert np.array_equal(rec["rule_flags"], flags.cpu().numpy().view(np.uint16)), t
+        assert np.array_equal(rec["region_map"], rmap.cpu().numpy()) and np.array_equal(rec["region_fit"], rfit.cpu().numpy()), t
+        for k, ten in (("current_step", b.step_count), ("agent_location", b.agent_xy), ("reward_code", b.reward_code),
+                       ("terminated", b.terminated), ("truncated", b.truncated), ("legal_mask", b.legal_mask)):
+            assert np.array_equal(rec[k], ten.cpu().numpy()), (t, k)
+        assert all(torch.equal(a.obs[k], b.obs[k]) for k in a.obs), t
+
+    rec = a.reset_info_host(idx)
+    b.reset(puzzle_idx=idx)
+    check(rec, "reset")
+    for t in range(60):
+        act = rng.integers(0, 4, n).astype(np.int32)
+        if t % 7 == 3:
+            act[rng.integers(0, n)] = -1 if t % 2 else 7
+        rec = a.step_info_host(act)
+        b.step(torch.from_numpy(act).cuda())
+        check(rec, t)
+        if t == 30:
+            rec = a.reset_info_host(None)                   # NULL = every env's current puzzle
+            b.reset()
+            check(rec, "reset 2")
+    assert torch.equal(a.stats(), b.stats()) and int(a.stats()[4]) == 60 * n
 
 
 def test_long_episodes_hit_max_steps_like_the_emulation():

@@ -20,7 +20,8 @@ for n in [int(a) for a in sys.argv[1:]] or [4096]:
         os.environ["SPARC_HOST_ZERO_COPY"] = spin
         env = SparcVecEnv(store, n, traceback=False, max_steps=1000, autoreset_mode="same_step", validate="terminal")
         env.reset()
-        a = torch.randint(0, 4, (n,), dtype=torch.uint8).pin_memory()
+        A = torch.randint(0, 4, (K, n), dtype=torch.uint8).pin_memory()      # fresh actions every call (one vector repeated walks every env into a wall)
+        a = A[0]
         r = torch.empty(n, dtype=torch.float32).pin_memory()
         te = torch.empty(n, dtype=torch.uint8).pin_memory()
         tr = torch.empty(n, dtype=torch.uint8).pin_memory()
@@ -30,16 +31,16 @@ for n in [int(a) for a in sys.argv[1:]] or [4096]:
         best = 1e9
         for _ in range(3):
             t0 = time.perf_counter()
-            for _ in range(K):
-                env.step_host(a, r, te, tr)
+            for t in range(K):
+                env.step_host(A[t], r, te, tr)
             torch.cuda.synchronize()
             best = min(best, (time.perf_counter() - t0) / K)
         # the bare ctypes call with prepared arguments: what the Python wrapper adds
-        args = (env.handle, a.data_ptr(), r.data_ptr(), te.data_ptr(), tr.data_ptr(), env._obs_ref, env._stream())
+        args = [(env.handle, A[t].data_ptr(), r.data_ptr(), te.data_ptr(), tr.data_ptr(), env._obs_ref, env._stream()) for t in range(K)]
         f = env.lib.sparc_step_host
         t0 = time.perf_counter()
-        for _ in range(K):
-            f(*args)
+        for t in range(K):
+            f(*args[t])
         torch.cuda.synchronize()
         bare = (time.perf_counter() - t0) / K
         if hasattr(env.lib, "sparc_debug_hosttiming"):          # -DHOST_TIMING builds: where the C call spends its time

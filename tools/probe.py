@@ -3,7 +3,7 @@
 Each positional argument is one arm: space-separated tokens, UPPERCASE=value are environment knobs of the library
 (read by sparc_env_create: SPARC_TILE, SPARC_SPLIT, SPARC_ENC_TILE, SPARC_VAL_GRID, ...), lowercase=value are
 workload=config2|config3|config4  envs=N  validate=terminal|never  format=reference|compact  update=rewrite|delta
-steps=K  obs=0 (no observation: dynamics only).  The K steps are one CUDA graph (as in bench.py), replayed `reps` times, best and median reported.
+steps=K  obs=0 (no observation: dynamics only)  graph=0 (the K steps launched from Python).  The K steps are one CUDA graph (as in bench.py), replayed `reps` times, best and median reported.
 
     gpurun -- 'python tools/probe.py "workload=config2" "workload=config2 SPARC_TILE=8" "workload=config2 validate=never"'
 
@@ -33,7 +33,7 @@ def store_for(cfg, pool_n):
 
 
 def run_arm(arm, reps=5):
-    opts = {"workload": "config4", "validate": "terminal", "format": "reference", "update": "rewrite", "steps": "200", "obs": "1"}
+    opts = {"workload": "config4", "validate": "terminal", "format": "reference", "update": "rewrite", "steps": "200", "obs": "1", "graph": "1"}
     envs = {}
     for tok in arm.split():
         k, v = tok.split("=", 1)
@@ -55,20 +55,26 @@ def run_arm(arm, reps=5):
     for t in range(W):
         env.step(actions[t])
     torch.cuda.synchronize()
-    side = torch.cuda.Stream()
-    side.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(side):
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph, stream=side):
-            for t in range(W, W + K):
-                env.step(actions[t])
-    torch.cuda.current_stream().wait_stream(side)
+    graph = None
+    if opts["graph"] != "0":
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                for t in range(W, W + K):
+                    env.step(actions[t])
+        torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ms = []
     for _ in range(reps):
         ev0.record()
-        graph.replay()
+        if graph is not None:
+            graph.replay()
+        else:
+            for t in range(W, W + K):
+                env.step(actions[t])
         ev1.record()
         torch.cuda.synchronize()
         ms.append(ev0.elapsed_time(ev1) / K)
