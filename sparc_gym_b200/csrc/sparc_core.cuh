@@ -12,8 +12,10 @@
 
 #if defined(SPARC_EMU_COUNTERS)
 static long long g_fit_iters = 0, g_fit_calls = 0, g_fit_max = 0, g_fit_cur = 0;   // search effort of exact_fit (tests only)
+static long long g_fit_hist[24];                                                   // searches by floor(log2(nodes)) (a call is booked when the next one begins)
+static inline void sparc_fit_book() { if (g_fit_cur > 0) { int b = 0; for (long long v = g_fit_cur; v > 1; v >>= 1) b++; g_fit_hist[b < 23 ? b : 23]++; } }
 #define SPARC_COUNT_FIT() (++g_fit_iters, ++g_fit_cur, g_fit_max = g_fit_cur > g_fit_max ? g_fit_cur : g_fit_max)
-#define SPARC_COUNT_FIT_CALL() (++g_fit_calls, g_fit_cur = 0)
+#define SPARC_COUNT_FIT_CALL() (sparc_fit_book(), ++g_fit_calls, g_fit_cur = 0)
 #else
 #define SPARC_COUNT_FIT() ((void)0)
 #define SPARC_COUNT_FIT_CALL() ((void)0)

@@ -156,6 +156,10 @@ int emu_exact_fit_split(uint64_t region, int w, int h, const SparcShape* shapes,
     if (iters) *iters = g_fit_iters;
     return ok ? 1 : 0;
 }
+void emu_fit_hist(long long* out24, int reset) {
+    sparc_fit_book(); g_fit_cur = 0;
+    for (int k = 0; k < 24; k++) { out24[k] = g_fit_hist[k]; if (reset) g_fit_hist[k] = 0; }
+}
 long long emu_fit_iters(int reset) { long long v = g_fit_iters; if (reset) g_fit_iters = 0; return v; }
 void emu_fit_counters(long long* out3, int reset) {
     out3[0] = g_fit_iters; out3[1] = g_fit_calls; out3[2] = g_fit_max;

@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
 
 
-def run(n_dense, steps):
+def run(n_dense, steps, agent="perfect"):
     import numpy as np
     import torch
     from fuzzrows import solution_actions
@@ -38,7 +38,7 @@ def run(n_dense, steps):
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
     warm = 100                                       # solutions differ in length: the envs desynchronise on their own
     for t in range(warm + steps):
-        a = table[pz, t_idx]
+        a = table[pz, t_idx] if agent == "perfect" else torch.randint(0, 4, (N,), dtype=torch.uint8, device="cuda")
         if t >= warm:
             ev[t - warm].record()
         _, _, te, tr, _ = env.step(a)
@@ -49,7 +49,7 @@ def run(n_dense, steps):
     torch.cuda.synchronize()
     ms = np.array([ev[t].elapsed_time(ev[t + 1]) for t in range(steps)])
     st = env.stats().cpu().numpy()
-    print(f"dense boards {n_dense}/{n_pz}: "
+    print(f"{agent} agent, SPARC_LINGER_BUDGET={os.environ.get('SPARC_LINGER_BUDGET', 'default')}, dense boards {n_dense}/{n_pz}: "
           f"step ms median {np.median(ms):.3f} p99 {np.percentile(ms, 99):.3f} max {ms.max():.3f} "
           f"(incl. the torch policy ops); episodes {st[0]}, solved {st[1]}, rules_pass {st[7]}")
 
@@ -59,9 +59,11 @@ if __name__ == "__main__":
     ap.add_argument("--dense", type=int, default=41)
     ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--run", action="store_true")
+    ap.add_argument("--agent", default="perfect", choices=["perfect", "random"],
+                    help="perfect: every env replays its listed solution (every episode ends in a full validation); random: uniform actions")
     a = ap.parse_args()
     if a.run:
-        run(a.dense, a.steps)
+        run(a.dense, a.steps, a.agent)
     else:
         for dense in (0, a.dense):
-            subprocess.run([sys.executable, os.path.abspath(__file__), "--run", "--dense", str(dense), "--steps", str(a.steps)])
+            subprocess.run([sys.executable, os.path.abspath(__file__), "--run", "--dense", str(dense), "--steps", str(a.steps), "--agent", a.agent])
