@@ -8,8 +8,13 @@
 //   k_encode  state -> observation: a CTA owns a tile of 8 consecutive envs, stages their bit-packed planes
 //             in shared memory and expands them into the caller's int32/int64 tensors with coalesced
 //             16-byte streaming stores.  HBM-write bound: X*Y*(4P+4+8) bytes per env-step.
-// Small batches use the fused k_env (one launch, one tile per CTA).
-// The device functions themselves (dynamics, validator, encoder) live in sparc_core.cuh.
+// With update = SPARC_OBS_DELTA the step is k_dyn (touches the changed cells in place) + k_post (warp-cooperative
+// validation of the queued terminal states and the full rewrite of the envs that began a new episode).
+// Small batches use the fused k_env (one launch, one tile per CTA: phase A in warp 0, then warps 0-2 encode while warp 3
+// validates the tile's terminal states); k_env_host is the same launch for sparc_step_host (actions in the kernel
+// parameters, results + completion flag into mapped host memory); k_info is the single-env drop-in's whole step.
+// The device functions themselves (dynamics, validator, encoder) live in sparc_core.cuh, the warp-cooperative
+// validator in sparc_val_warp.cuh.
 #include <cuda_runtime.h>
 #include <nvtx3/nvToolsExt.h>          // header-only NVTX 3: ranges around the ABI calls when SPARC_NVTX=1 (Nsight Systems / ncu --nvtx)
 #include <stdio.h>
@@ -309,7 +314,7 @@ __device__ __forceinline__ void push_hard_item(const KParams& p, uint32_t slot) 
 }
 
 // Terminal validation BESIDE the full-rewrite encoder: one snapshot per thread, a small grid.  k_encode fills the
-// register file (9 CTAs x 56 registers x 128 threads per SM), so every validator CTA displaces encoder CTAs for as
+// register file (8 CTAs x 60 registers x 128 threads per SM), so every validator CTA displaces encoder CTAs for as
 // long as it runs; what counts here is snapshots per resident warp, not latency, and 32 diverging lanes that each
 // carry a snapshot get through ~2.5x more of them per warp-second than a converged warp that takes them one by one
 // (measured at 131,072 envs, ~2,230 snapshots per step, 32 CTAs: this kernel 20-50 us alone, the warp-per-snapshot
