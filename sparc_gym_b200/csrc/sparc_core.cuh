@@ -1172,10 +1172,16 @@ SPARC_HD void expand_info_i32(const StoreDev& st, const uint32_t* rows, const ui
         int32_t v[4] = {0, 0, 0, 0};
         if (m) {
             int j = (int)sp_umulhi(e0, st.inv_S), r = (int)e0 - j * S;
+            if (r + 3 < S) {                                     // the four elements belong to one env: one base address
+                const int32_t* ip = st.info + ((size_t)tile_puzzle[j] * S + r);
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                if ((m >> u) & 1u) v[u] = sp_ldg(st.info + (size_t)tile_puzzle[j] * S + r);
-                if (++r >= S) { r = 0; j++; }
+                for (int u = 0; u < 4; u++) if ((m >> u) & 1u) v[u] = sp_ldg(ip + u);
+            } else {
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    if ((m >> u) & 1u) v[u] = sp_ldg(st.info + (size_t)tile_puzzle[j] * S + r);
+                    if (++r >= S) { r = 0; j++; }
+                }
             }
         }
         sp_st4(out_tile + 4 * (size_t)c, v[0], v[1], v[2], v[3]);
