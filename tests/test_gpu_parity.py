@@ -130,13 +130,15 @@ def test_checkpoint_restore_and_standalone_encode():
         assert all(torch.equal(ra[0][k], rb[0][k]) for k in ra[0])
 
 
-def test_step_host_matches_device_step():
-    """sparc_step_host (host action / result buffers, result copies overlapped with the encoder on the
-    split path) returns exactly what the device-buffer step returns."""
+@pytest.mark.parametrize("obs_update", ["rewrite", "delta"])
+def test_step_host_matches_device_step(obs_update):
+    """sparc_step_host (host action / result buffers: packed launch + completion flag on the fused kernel; result copies
+    beside the encoder on the split path; results written into the pinned arrays by k_dyn itself in the delta step)
+    returns exactly what the device-buffer step returns."""
     rows = gen_pool(16, [(4, 4), (6, 6)], RULES_FULL, seed0=500)
     for n in (40000, 300):                      # split pipeline / fused kernel
-        a = make_env(rows, n, traceback=False, max_steps=20, autoreset_mode="same_step")
-        b = make_env(rows, n, traceback=False, max_steps=20, autoreset_mode="same_step")
+        a = make_env(rows, n, traceback=False, max_steps=20, autoreset_mode="same_step", obs_update=obs_update)
+        b = make_env(rows, n, traceback=False, max_steps=20, autoreset_mode="same_step", obs_update=obs_update)
         a.reset(); b.reset()
         rng = np.random.default_rng(n)
         r = torch.empty(n, dtype=torch.float32).pin_memory()
