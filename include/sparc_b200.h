@@ -216,7 +216,7 @@ int sparc_env_destroy(SparcEnv* env);
  * puzzle index per env (taken modulo n_puzzles, Python style: -1 is the last puzzle; the indices live on
  * the device, so a range error cannot be reported without a sync -- host wrappers check before uploading),
  * or NULL = keep the env's current puzzle.  A freshly created env is already a clean reset on puzzle
- * i mod n_puzzles.  Every entry point selects the store's device itself (cudaSetDevice).
+ * i mod n_puzzles.  Every entry point works on the store's device and leaves the calling thread's current device as it was.
  * mask_dev: uint8[n_envs] which envs to reset, or NULL = all.  Writes the observation of all envs. */
 int sparc_reset(SparcEnv* env, const int32_t* puzzle_idx_dev, const uint8_t* mask_dev,
                 const SparcStepOut* info_out, const SparcObsOut* obs, void* stream);

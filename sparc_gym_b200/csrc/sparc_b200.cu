@@ -585,6 +585,18 @@ __global__ void k_read_stats(unsigned long long* stats, long long* out, int clea
     if (lane == 0) out[k] = (long long)v;
 }
 
+// Every entry point works on the store's device and leaves the calling thread's current device as it found it (a
+// caller with several GPUs in one process -- or torch, which reads the current device back -- must not see it move).
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int dev) {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != dev) err = cudaSetDevice(dev); else prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 // ---------------------------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------------------------
@@ -611,7 +623,7 @@ int sparc_store_create(const SparcStoreDesc* desc, int device, SparcStore** out)
         return fail(SPARC_E_ARG, "bad store geometry%s");
     if (desc->plane_ids[0] != SPARC_PL_VISITED || desc->plane_ids[2] != SPARC_PL_AGENT)
         return fail(SPARC_E_ARG, "planes 0 and 2 must be visited and agent_location%s");
-    CU(cudaSetDevice(device));
+    DeviceGuard dg_(device); CU(dg_.err);
     SparcStore* s = new (std::nothrow) SparcStore();
     if (!s) return fail(SPARC_E_NOMEM, "out of host memory%s");
     memset(s, 0, sizeof(*s));
@@ -682,7 +694,7 @@ int sparc_store_create(const SparcStoreDesc* desc, int device, SparcStore** out)
 
 int sparc_store_destroy(SparcStore* s) {
     if (!s) return SPARC_OK;
-    cudaSetDevice(s->device);
+    DeviceGuard dg_(s->device);
     for (void* b : s->blocks) if (b) cudaFree(b);
     delete s;
     return SPARC_OK;
@@ -706,7 +718,7 @@ int sparc_env_create(SparcStore* store, int64_t n_envs, int traceback, int max_s
     if (!store || !out || n_envs <= 0) return fail(SPARC_E_ARG, "bad argument%s");
     if (autoreset_mode < 0 || autoreset_mode > 3 || validate_mode < 0 || validate_mode > 2 || puzzle_stride < 0)
         return fail(SPARC_E_ARG, "bad mode%s");
-    CU(cudaSetDevice(store->device));
+    DeviceGuard dg_(store->device); CU(dg_.err);
     SparcEnv* e = new (std::nothrow) SparcEnv();
     if (!e) return fail(SPARC_E_NOMEM, "out of host memory%s");
     memset(e, 0, sizeof(*e));
@@ -804,7 +816,7 @@ int sparc_env_create(SparcStore* store, int64_t n_envs, int traceback, int max_s
 
 int sparc_env_destroy(SparcEnv* e) {
     if (!e) return SPARC_OK;
-    cudaSetDevice(e->store->device);
+    DeviceGuard dg_(e->store->device);
     void* ptrs[] = {e->s.core, e->s.vis, e->s.ep_ret, e->s.moves, e->s.stats, e->vq_count, e->vq, e->hq_count, e->hq, e->rq_count, e->rq, e->act_stage, e->rew_stage, e->term_stage, e->trunc_stage, e->info_stage, e->int_stage, e->done_count, e->packed_dev};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (e->done_host) cudaFreeHost((void*)e->done_host);
@@ -823,7 +835,7 @@ int sparc_env_destroy(SparcEnv* e) {
 }
 
 static int launch_env(SparcEnv* e, KParams& p, void* stream) {
-    CU(cudaSetDevice(e->store->device));          // raw C-ABI callers on multi-GPU hosts need not do it themselves
+    DeviceGuard dg_(e->store->device); CU(dg_.err);   // raw C-ABI callers on multi-GPU hosts need not select the device themselves
     p.st = e->store->d; p.sd = e->s; p.cfg = e->cfg; p.tile = e->tile;
     const int64_t n = e->cfg.n_envs;
     if (p.obs.format != SPARC_OBS_REFERENCE && p.obs.format != SPARC_OBS_COMPACT) return fail(SPARC_E_ARG, "bad observation format%s");
@@ -954,7 +966,7 @@ int sparc_step(SparcEnv* e, const void* actions_dev, int action_dtype, const Spa
 int sparc_encode(SparcEnv* e, const SparcObsOut* obs, void* stream) {
     NvtxRange nvtx_("sparc_encode");
     if (!e || !obs) return fail(SPARC_E_ARG, "null argument%s");
-    CU(cudaSetDevice(e->store->device));
+    DeviceGuard dg_(e->store->device); CU(dg_.err);
     KParams p; memset(&p, 0, sizeof(p));
     p.st = e->store->d; p.sd = e->s; p.cfg = e->cfg; p.obs = *obs;
     const int64_t n = e->cfg.n_envs;
@@ -974,7 +986,7 @@ int sparc_validate(SparcEnv* e, const uint8_t* mask_dev, uint16_t* flags_dev, in
                    int8_t* region_fit_dev, void* stream) {
     NvtxRange nvtx_("sparc_validate");
     if (!e) return fail(SPARC_E_ARG, "null env%s");
-    CU(cudaSetDevice(e->store->device));
+    DeviceGuard dg_(e->store->device); CU(dg_.err);
     const int64_t n = e->cfg.n_envs;
     k_validate<<<(unsigned)((n + CTA_THREADS - 1) / CTA_THREADS), CTA_THREADS, 0, (cudaStream_t)stream>>>(
         e->store->d, e->s, n, mask_dev, flags_dev, region_map_dev, region_fit_dev);
@@ -985,7 +997,7 @@ int sparc_validate(SparcEnv* e, const uint8_t* mask_dev, uint16_t* flags_dev, in
 
 int sparc_stats(SparcEnv* e, int64_t* out_dev, int clear, void* stream) {
     if (!e || !out_dev) return fail(SPARC_E_ARG, "null argument%s");
-    CU(cudaSetDevice(e->store->device));
+    DeviceGuard dg_(e->store->device); CU(dg_.err);
     k_read_stats<<<1, 32 * SPARC_N_STATS, 0, (cudaStream_t)stream>>>(e->s.stats, (long long*)out_dev, clear);
     CU(cudaGetLastError());
     e->launches++;
@@ -1014,7 +1026,7 @@ int sparc_step_host(SparcEnv* e, const uint8_t* actions_host, float* reward_host
                     uint8_t* truncated_host, const SparcObsOut* obs, void* stream) {
     NvtxRange nvtx_("sparc_step_host");
     if (!e || !actions_host) return fail(SPARC_E_ARG, "null argument%s");
-    CU(cudaSetDevice(e->store->device));
+    DeviceGuard dg_(e->store->device); CU(dg_.err);
     cudaStream_t s = (cudaStream_t)stream;
     const size_t n = (size_t)e->cfg.n_envs;
     SparcStepOut out; memset(&out, 0, sizeof(out));
@@ -1108,7 +1120,7 @@ int64_t sparc_info_record_bytes(const SparcEnv* e) {
 static int info_call(SparcEnv* e, bool reset, const int32_t* ints_host, void* record_host, const SparcObsOut* obs, void* stream) {
     NvtxRange nvtx_("sparc_info_host");
     if (!e || !record_host || (!reset && !ints_host)) return fail(SPARC_E_ARG, "null argument%s");
-    CU(cudaSetDevice(e->store->device));
+    DeviceGuard dg_(e->store->device); CU(dg_.err);
     cudaStream_t s = (cudaStream_t)stream;
     const size_t n = (size_t)e->cfg.n_envs, bytes = (size_t)sparc_info_record_bytes(e);
     if (n <= SPARC_INFO_MAX_ENVS && e->done_host && obs &&
@@ -1187,7 +1199,7 @@ int64_t sparc_state_bytes(const SparcEnv* e) {
 }
 
 static int state_copy(SparcEnv* e, char* blob, bool save, void* stream) {
-    CU(cudaSetDevice(e->store->device));
+    DeviceGuard dg_(e->store->device); CU(dg_.err);
     const size_t n = (size_t)e->cfg.n_envs;
     struct { void* p; size_t bytes; } parts[] = {{e->s.core, n * 16}, {e->s.vis, n * 32}, {e->s.ep_ret, n * 4},
                                                  {e->s.moves, e->s.moves ? n * SPARC_MOVE_WORDS * 4 : 0}};

@@ -19,6 +19,9 @@ from .ingest import ingest_rows
 from .store import PuzzleStore
 
 
+_ACT_CODES = {torch.uint8: abi.ACT_DTYPES["uint8"], torch.int32: abi.ACT_DTYPES["int32"], torch.int64: abi.ACT_DTYPES["int64"]}
+
+
 class DeviceStore:
     """A PuzzleStore uploaded to one GPU (SparcStore handle)."""
 
@@ -119,6 +122,7 @@ class SparcVecEnv:
                                      self.step_count.data_ptr(), self.agent_xy.data_ptr())
         self.write_obs = write_obs
         self._obs_ref, self._no_obs_ref = C.byref(self._obs_out), C.byref(self._no_obs)
+        self._step_ref = C.byref(self._step_out)
 
     # -- helpers
     def _stream(self):
@@ -153,16 +157,19 @@ class SparcVecEnv:
         """One lockstep step (SG.py:1111-1238).  `actions`: uint8/int32/int64 CUDA tensor [N]."""
         if not (isinstance(actions, torch.Tensor) and actions.is_cuda):
             actions = torch.as_tensor(actions, device=self.device)
-        name = str(actions.dtype).replace("torch.", "")
-        if name not in abi.ACT_DTYPES:
-            actions, name = actions.to(torch.int64), "int64"
-        actions = actions.contiguous()
+        code = _ACT_CODES.get(actions.dtype)
+        if code is None:
+            actions, code = actions.to(torch.int64), abi.ACT_DTYPES["int64"]
+        if not actions.is_contiguous():
+            actions = actions.contiguous()
         if actions.numel() != self.num_envs:
             raise ValueError("actions must have one entry per env")
-        with torch.cuda.device(self.device):
-            abi.check(self.lib.sparc_step(self.handle, actions.data_ptr(), abi.ACT_DTYPES[name],
-                                          C.byref(self._step_out),
-                                          C.byref(self._obs_out if self.write_obs else self._no_obs), self._stream()))
+        # (no torch.cuda.device() context: the library selects the store's device itself; on launch-bound batches the
+        # context manager, the dtype-name string and two fresh byref objects were a third of the call)
+        rc = self.lib.sparc_step(self.handle, actions.data_ptr(), code, self._step_ref,
+                                 self._obs_ref if self.write_obs else self._no_obs_ref, self._stream())
+        if rc:
+            abi.check(rc)
         return self.obs, self.reward, self.terminated, self.truncated, self._info()
 
     def step_host(self, actions_host, reward_host, terminated_host, truncated_host):
