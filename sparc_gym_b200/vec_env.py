@@ -121,8 +121,8 @@ class SparcVecEnv:
                                      self.legal_mask.data_ptr(), self.rule_flags.data_ptr(),
                                      self.step_count.data_ptr(), self.agent_xy.data_ptr())
         self.write_obs = write_obs
-        self._obs_ref, self._no_obs_ref = C.byref(self._obs_out), C.byref(self._no_obs)
-        self._step_ref = C.byref(self._step_out)
+        self._obs_p, self._no_obs_p = C.byref(self._obs_out), C.byref(self._no_obs)
+        self._step_p = C.byref(self._step_out)
 
     # -- helpers
     def _stream(self):
@@ -166,8 +166,8 @@ class SparcVecEnv:
             raise ValueError("actions must have one entry per env")
         # (no torch.cuda.device() context: the library selects the store's device itself; on launch-bound batches the
         # context manager, the dtype-name string and two fresh byref objects were a third of the call)
-        rc = self.lib.sparc_step(self.handle, actions.data_ptr(), code, self._step_ref,
-                                 self._obs_ref if self.write_obs else self._no_obs_ref, self._stream())
+        rc = self.lib.sparc_step(self.handle, actions.data_ptr(), code, self._step_p,
+                                 self._obs_p if self.write_obs else self._no_obs_p, self._stream())
         if rc:
             abi.check(rc)
         return self.obs, self.reward, self.terminated, self.truncated, self._info()
@@ -179,7 +179,7 @@ class SparcVecEnv:
         # (no torch.cuda.device() context here: the library selects the store's device itself, and on a launch-bound
         # batch the context manager alone was a tenth of the call)
         rc = self.lib.sparc_step_host(self.handle, ptr(actions_host), ptr(reward_host), ptr(terminated_host), ptr(truncated_host),
-                                      self._obs_ref if self.write_obs else self._no_obs_ref, self._stream())
+                                      self._obs_p if self.write_obs else self._no_obs_p, self._stream())
         if rc:
             abi.check(rc)
 

@@ -36,7 +36,7 @@ for n in [int(a) for a in sys.argv[1:]] or [4096]:
             torch.cuda.synchronize()
             best = min(best, (time.perf_counter() - t0) / K)
         # the bare ctypes call with prepared arguments: what the Python wrapper adds
-        args = [(env.handle, A[t].data_ptr(), r.data_ptr(), te.data_ptr(), tr.data_ptr(), env._obs_ref, env._stream()) for t in range(K)]
+        args = [(env.handle, A[t].data_ptr(), r.data_ptr(), te.data_ptr(), tr.data_ptr(), env._obs_p, env._stream()) for t in range(K)]
         f = env.lib.sparc_step_host
         t0 = time.perf_counter()
         for t in range(K):
