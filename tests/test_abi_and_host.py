@@ -50,6 +50,25 @@ def test_no_compute_without_a_device_and_no_cpu_fallback():
     assert b"cuda" in lib.sparc_last_error().lower()
 
 
+def test_product_package_never_touches_the_checkers():
+    """The oracle, the host build of the device code (tests/emu), the staged reference (baseline/_ref) and
+    /root/reference are test / bench infrastructure: nothing under sparc_gym_b200/ or in the CUDA sources may import,
+    load or name them -- a product path that routes through a checker voids every parity claim."""
+    import re
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "sparc_gym_b200")
+    bad = re.compile(r"oracle|libsparc_emu|tests[/.]emu|emu_env|baseline|_ref\b|/root/reference|refharness")
+    hits = []
+    for dirpath, _, names in os.walk(root):
+        for name in names:
+            if name.endswith((".py", ".cu", ".cuh", ".h")):
+                path = os.path.join(dirpath, name)
+                for ln, line in enumerate(open(path, encoding="utf-8"), 1):
+                    line = line.split("#" if name.endswith(".py") else "//")[0]          # (comments may explain the set-up)
+                    if bad.search(line):
+                        hits.append(f"{os.path.relpath(path, root)}:{ln}: {line.strip()[:100]}")
+    assert not hits, "\n".join(hits)
+
+
 def test_struct_layouts_match_the_header():
     assert HEADER_DTYPE.itemsize == 32 and SHAPE_DTYPE.itemsize == 32
     # StoreDesc: 17 int32 (padded to 72 bytes) + 9 pointers, exactly as a C compiler lays it out
