@@ -104,6 +104,25 @@ def test_encoder_is_tiling_invariant_and_handles_tiny_lattices():
                 compare(env.step(a), orc.expected(), f"tile={tile} step {t}")
 
 
+def test_start_node_on_a_gap_cannot_be_traced_back_to():
+    """SG.py:1024-1051 tests `gaps` for every candidate move, the traceback target included: an episode whose start node
+    is itself marked as a gap can leave it but never undo back onto it (legality works on walk & ~visited plus a
+    walkable-`path[-2]` test: this is the one case where that test says no)."""
+    import yaml
+    rows = []
+    for seed in range(6):
+        row = dict(gen_puzzle(3, 3, 40 + seed, RULES_GAPS_DOTS))
+        tv = yaml.safe_load(row["text_visualization"])
+        st = tv["puzzle"]["start"]
+        tv["puzzle"]["cells"] = [c for c in tv["puzzle"]["cells"] if c["position"] != st] + \
+            [{"position": dict(st), "properties": {"gap": True}}]
+        row["text_visualization"] = yaml.safe_dump(tv)
+        row["id"] = f"gapstart-{seed}"
+        rows.append(row)
+    env, orc = run_lockstep(EmuVecEnv, rows, 24, 40, True, 30, "next_step", "every_step", seed=8, follow=0.2)
+    assert env.stats()[0] > 0
+
+
 def max_size_rows():
     """Pools at the ingest limit (7x7 cells = 15x15 lattice, SPARC_MAX_DIM) and non-square boards next to it:
     generated full-rule puzzles plus fuzz rows (shape ids colliding with triangle counts, Q10); fuzz rows over
