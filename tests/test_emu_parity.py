@@ -104,10 +104,7 @@ def test_encoder_is_tiling_invariant_and_handles_tiny_lattices():
                 compare(env.step(a), orc.expected(), f"tile={tile} step {t}")
 
 
-def test_start_node_on_a_gap_cannot_be_traced_back_to():
-    """SG.py:1024-1051 tests `gaps` for every candidate move, the traceback target included: an episode whose start node
-    is itself marked as a gap can leave it but never undo back onto it (legality works on walk & ~visited plus a
-    walkable-`path[-2]` test: this is the one case where that test says no)."""
+def gap_start_rows():
     import yaml
     rows = []
     for seed in range(6):
@@ -119,7 +116,14 @@ def test_start_node_on_a_gap_cannot_be_traced_back_to():
         row["text_visualization"] = yaml.safe_dump(tv)
         row["id"] = f"gapstart-{seed}"
         rows.append(row)
-    env, orc = run_lockstep(EmuVecEnv, rows, 24, 40, True, 30, "next_step", "every_step", seed=8, follow=0.2)
+    return rows
+
+
+def test_start_node_on_a_gap_cannot_be_traced_back_to():
+    """SG.py:1024-1051 tests `gaps` for every candidate move, the traceback target included: an episode whose start node
+    is itself marked as a gap can leave it but never undo back onto it (legality works on walk & ~visited plus a
+    walkable-`path[-2]` test: this is the one case where that test says no)."""
+    env, orc = run_lockstep(EmuVecEnv, gap_start_rows(), 24, 40, True, 30, "next_step", "every_step", seed=8, follow=0.2)
     assert env.stats()[0] > 0
 
 

@@ -29,6 +29,12 @@ def test_fuzz_rows_every_step_validation(traceback):
     run_lockstep(make_env, rows, 36, 45, traceback, 40, "disabled", "every_step", seed=3)
 
 
+def test_start_node_on_a_gap_cannot_be_traced_back_to():
+    from test_emu_parity import gap_start_rows
+    env, _ = run_lockstep(make_env, gap_start_rows(), 24, 40, True, 30, "next_step", "every_step", seed=8, follow=0.2)
+    assert int(env.stats()[0]) > 0
+
+
 def test_full_rules_mixed_sizes_terminal_validation():
     rows = gen_pool(8, [(3, 3), (4, 4), (5, 5), (6, 6)], RULES_FULL, seed0=40, extra_solutions=1)
     run_lockstep(make_env, rows, 24, 90, True, 80, "disabled", "terminal", seed=5, follow=0.97)
